@@ -1,0 +1,88 @@
+"""Deterministic, integer-only synthetic near/far int16 streams.
+
+Every sample is a pure function of (seed, instance, sample index): a counter-based 32-bit hash drives
+white noise, a burst envelope makes it speech-like (on/off segments of 0.25 s with amplitudes from a
+small table, digital silence included), and the near end is a delayed, filtered copy of the far end
+(an integer 3-tap echo path with per-instance gain) plus near-end noise and occasional double talk.
+No floating point is involved, so host and device always see identical bits.
+
+``kind='echo'``   the moderate family used by the throughput bench and most parity tests
+``kind='stress'`` adds full-scale / clipping / exact-zero segments on both ends (exercises the
+                  saturation, Q-realignment and min-statistics branches listed in SURVEY.md 8c)
+"""
+from __future__ import annotations
+
+import numpy as np
+
+_AMP_ECHO = np.array([0, 0, 30, 500, 3000, 6000, 12000, 20000], dtype=np.int64)
+_AMP_STRESS = np.array([0, 0, 1, 30, 6000, 20000, 32767, 40000], dtype=np.int64)
+
+
+def _hash32(x: np.ndarray) -> np.ndarray:
+    """lowbias32 integer hash on uint32 arrays (wraps mod 2**32)."""
+    x = x.astype(np.uint32, copy=True)
+    x ^= x >> np.uint32(16)
+    x *= np.uint32(0x7FEB352D)
+    x ^= x >> np.uint32(15)
+    x *= np.uint32(0x846CA68B)
+    x ^= x >> np.uint32(16)
+    return x
+
+
+def _noise16(seed: int, inst: np.ndarray, t: np.ndarray, salt: int) -> np.ndarray:
+    key = (np.uint32(seed & 0xFFFFFFFF) ^ (inst.astype(np.uint32) * np.uint32(0x9E3779B9))
+           ^ (t.astype(np.uint32) * np.uint32(0x85EBCA6B)) ^ np.uint32(salt))
+    return (_hash32(key) >> np.uint32(16)).astype(np.int64) - 32768
+
+
+def synth_streams(n_instances: int, n_samples: int, fs: int = 16000, seed: int = 0xAEC0,
+                  delay_ms=40, kind: str = "echo", first_instance: int = 0, first_sample: int = 0):
+    """Return (far, near) int16 arrays of shape [n_instances, n_samples].
+
+    ``delay_ms`` is a scalar or a per-instance array: the acoustic echo delay in ms.
+    ``first_instance``/``first_sample`` let shards/chunks generate their slice of one global stream.
+    """
+    with np.errstate(over="ignore"):
+        inst = (np.arange(n_instances, dtype=np.int64) + first_instance)[:, None]
+        delay = np.broadcast_to(np.asarray(delay_ms, dtype=np.int64), (n_instances,))[:, None] * (fs // 1000)
+        max_d = int(delay.max()) + 4
+        # generate the far end with a pre-roll so the delayed copy exists from sample 0
+        t = (np.arange(-max_d, n_samples, dtype=np.int64) + first_sample)[None, :]
+        seg = np.floor_divide(t, fs // 4)
+        amp_tab = _AMP_STRESS if kind == "stress" else _AMP_ECHO
+        sel = _hash32((inst.astype(np.uint32) * np.uint32(0x632BE5AB)) ^ (seg.astype(np.uint32) * np.uint32(0x2545F491))
+                      ^ np.uint32(seed & 0xFFFFFFFF))
+        amp = amp_tab[(sel >> np.uint32(7)) % np.uint32(len(amp_tab))]
+        raw = _noise16(seed, inst, t, 0x1234567)
+        # mild low-pass so the spectrum is not flat: y[t] = (x[t] + x[t-1]) / 2 (first column kept)
+        lp = raw.copy()
+        lp[:, 1:] = (raw[:, 1:] + raw[:, :-1]) >> 1
+        far_full = np.clip((lp * amp) >> 15, -32768, 32767)
+        far_full[t.repeat(n_instances, 0) < 0] = 0  # nothing before the global stream start
+
+        idx = np.arange(n_samples, dtype=np.int64)[None, :] + max_d
+        g = 64 + (_hash32(inst.astype(np.uint32) * np.uint32(0x27D4EB2F) + np.uint32(seed & 0xFFFF)) % np.uint32(448)).astype(np.int64)
+        rows = np.arange(n_instances)[:, None]
+        e0 = far_full[rows, idx - delay]
+        e1 = far_full[rows, idx - delay - 1]
+        e3 = far_full[rows, idx - delay - 3]
+        echo = (g * e0 + (g >> 1) * e1 - (g >> 2) * e3) >> 8  # Q8 gains, 0.25 .. 2.0 main tap
+
+        tn = t[:, max_d:]
+        nseg = np.floor_divide(tn, fs // 2)
+        nsel = _hash32((inst.astype(np.uint32) * np.uint32(0x9E3779B1)) ^ (nseg.astype(np.uint32) * np.uint32(0x7F4A7C15))
+                       ^ np.uint32((seed >> 3) & 0xFFFFFFFF))
+        if kind == "stress":
+            ntab = np.array([0, 0, 0, 1, 3, 300, 32767, 50000], dtype=np.int64)
+        else:
+            ntab = np.array([0, 3, 30, 100, 300, 300, 4000, 100], dtype=np.int64)  # one double-talk level
+        namp = ntab[(nsel >> np.uint32(9)) % np.uint32(len(ntab))]
+        nnoise = (_noise16(seed ^ 0x5bd1e995, inst, tn, 0x7654321) * namp) >> 15
+        if kind == "stress":
+            # exact digital silence on the near end for some segments (echo muted too)
+            mute = ((nsel >> np.uint32(3)) % np.uint32(5)) == 0
+            echo = np.where(mute, 0, echo)
+            nnoise = np.where(mute, 0, nnoise)
+        near = np.clip(echo + nnoise, -32768, 32767)
+        far = far_full[:, max_d:]
+        return far.astype(np.int16), near.astype(np.int16)
