@@ -1,0 +1,102 @@
+/*
+ * aecm_b200.h -- batched C ABI of the B200-native AECM engine (libaecm_b200.so).
+ *
+ * A batch is N independent AECM instances resident on one GPU (one warp per instance, state in HBM).
+ * Every entry point below applies the *same* reference API call to a range of instances in lockstep, in a
+ * single kernel launch.  The per-instance semantics -- arguments, state machine, int16 output and return
+ * code -- are exactly those of the reference call named beside each function (reference file
+ * aecm/echo_control_mobile.h / .cc in cpuimage/WebRTC_AECM).  Plain C: pointers, sizes and integers only.
+ *
+ * Return value of every int32_t function: 0 when the call was issued; -1 for a NULL batch;
+ * AECM_NULL_POINTER_ERROR / AECM_BAD_PARAMETER_ERROR for bad arguments that the reference would reject for
+ * every instance alike; AECM_UNSPECIFIED_ERROR when CUDA failed (AecmB200_LastError() has the text).
+ * Per-instance return codes (0, AECM_UNINITIALIZED_ERROR, AECM_BAD_PARAMETER_WARNING, ...) are delivered
+ * in the optional status[] array, one int32 per instance of the range.
+ */
+#ifndef AECM_B200_H_
+#define AECM_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#include "echo_control_mobile.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct AecmB200Batch AecmB200Batch;
+
+/* N x { WebRtcAecm_Create (echo_control_mobile.h:46) } on CUDA device `device`.  NULL on failure. */
+AecmB200Batch *AecmB200_Create(int32_t nInstances, int32_t device);
+/* N x { WebRtcAecm_Free (:55) }.  NULL is a no-op. */
+void AecmB200_Free(AecmB200Batch *batch);
+int32_t AecmB200_NumInstances(const AecmB200Batch *batch);
+int32_t AecmB200_Device(const AecmB200Batch *batch);
+const char *AecmB200_LastError(const AecmB200Batch *batch);
+
+/* Returns instances [first, first+count) to the freshly created (zero-filled, un-initialised) state. */
+int32_t AecmB200_Reset(AecmB200Batch *batch, int32_t first, int32_t count);
+/* count x { WebRtcAecm_Init (:70) } on instances [first, first+count). */
+int32_t AecmB200_Init(AecmB200Batch *batch, int32_t first, int32_t count, int32_t sampFreq);
+/* count x { WebRtcAecm_set_config (:156) }. status: host array [count] or NULL. */
+int32_t AecmB200_SetConfig(AecmB200Batch *batch, int32_t first, int32_t count, AecmConfig config, int32_t *status);
+/* WebRtcAecm_InitEchoPath (:172) / WebRtcAecm_GetEchoPath (:191) for one instance (host buffers). */
+int32_t AecmB200_InitEchoPath(AecmB200Batch *batch, int32_t instance, const void *echo_path, size_t size_bytes);
+int32_t AecmB200_GetEchoPath(AecmB200Batch *batch, int32_t instance, void *echo_path, size_t size_bytes);
+
+/*
+ * The streaming call.  For every instance r of [first, first+count) and every call c of [0, nCalls):
+ *      if (farend && (!farendMask || farendMask[c*count + r]))
+ *          WebRtcAecm_BufferFarend(inst, farend + r*rowStride + c*nrOfSamples, nrOfSamples);        (:87)
+ *      if (nearendNoisy)
+ *          WebRtcAecm_Process(inst, nearendNoisy + r*rowStride + c*nrOfSamples,
+ *                             nearendClean ? nearendClean + ... : NULL, out + ..., nrOfSamples,
+ *                             msInSndCardBuf ? msInSndCardBuf[r] : msUniform);                        (:135-140)
+ * status[r] receives the first non-zero return code among those calls (0 if none).
+ * nCalls > 1 fuses consecutive 10 ms calls into one launch with the instance state held on-chip.
+ */
+typedef struct {
+    const int16_t *farend;        /* [count][rowStride] plane or NULL */
+    const int16_t *nearendNoisy;  /* [count][rowStride] plane or NULL */
+    const int16_t *nearendClean;  /* optional plane */
+    int16_t *out;                 /* [count][rowStride] plane (required with nearendNoisy) */
+    int64_t rowStride;            /* samples between instance rows; >= nCalls * nrOfSamples */
+    int32_t first, count;         /* instance range */
+    int32_t nrOfSamples;          /* 80 or 160, as in the reference */
+    int32_t nCalls;               /* >= 1 */
+    const int16_t *msInSndCardBuf;/* [count] or NULL */
+    int16_t msUniform;            /* used when msInSndCardBuf is NULL */
+    const uint8_t *farendMask;    /* optional [nCalls][count] */
+    int32_t *status;              /* optional [count] */
+} AecmB200StreamArgs;
+
+/* Host-memory planes: copies in, runs, copies out and waits (pinned planes avoid the staging copy). */
+int32_t AecmB200_ProcessStream(AecmB200Batch *batch, const AecmB200StreamArgs *hostArgs);
+/* Device-memory planes on the batch's GPU: enqueues on the batch stream and returns immediately. */
+int32_t AecmB200_ProcessStreamDevice(AecmB200Batch *batch, const AecmB200StreamArgs *deviceArgs);
+
+/* Lockstep mirrors of the two reference calls over the whole batch; planes are [N][nrOfSamples], host memory. */
+int32_t AecmB200_BufferFarend(AecmB200Batch *batch, const int16_t *farend, size_t nrOfSamples, int32_t *status);
+int32_t AecmB200_Process(AecmB200Batch *batch, const int16_t *nearendNoisy, const int16_t *nearendClean, int16_t *out,
+                         size_t nrOfSamples, const int16_t *msInSndCardBuf, int16_t msUniform, int32_t *status);
+
+/* stream plumbing: the batch owns a CUDA stream unless one is adopted (e.g. the caller's current stream) */
+int32_t AecmB200_Synchronize(AecmB200Batch *batch);
+void *AecmB200_CudaStream(const AecmB200Batch *batch);
+int32_t AecmB200_AdoptCudaStream(AecmB200Batch *batch, void *cudaStream);
+
+/* pinned host memory for the host-plane calls */
+void *AecmB200_HostAlloc(size_t bytes);
+void AecmB200_HostFree(void *p);
+
+/* introspection (tests, tooling) */
+size_t AecmB200_StateBytes(void);
+int32_t AecmB200_ReadState(AecmB200Batch *batch, int32_t instance, void *dst, size_t bytes);
+int64_t AecmB200_KernelLaunchCount(void);
+int32_t AecmB200_DeviceCount(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* AECM_B200_H_ */

@@ -101,3 +101,133 @@ def run_streams(far, near, *, fs=16000, samples_per_call=None, impl="oracle", cl
     if rc != 0:
         raise RuntimeError(f"oracle_run_streams rc={rc}")
     return out, ret, secs.value
+
+
+# ---------------------------------------------------------------------------------------------------
+# single-instance stepping + state mirror (stage-level parity / debugging)
+# ---------------------------------------------------------------------------------------------------
+class Fifo(C.Structure):
+    _fields_ = [("cap", C.c_int32), ("rd", C.c_int32), ("cnt", C.c_int32)]
+
+
+class OracleState(C.Structure):
+    """Mirror of ``OracleAecm`` in oracle/aecm_oracle.h."""
+    _fields_ = [
+        ("fs", C.c_int32), ("init_flag", C.c_int16), ("buf_size_start", C.c_int16), ("counter", C.c_int16),
+        ("sum", C.c_int16), ("first_val", C.c_int16), ("check_buf_size_ctr", C.c_int16),
+        ("ms_in_snd_card_buf", C.c_int16), ("filt_delay", C.c_int16), ("last_delay_diff", C.c_int16),
+        ("echo_mode", C.c_int16), ("time_for_delay_change", C.c_int32), ("ec_startup", C.c_int32),
+        ("check_buff_size", C.c_int32), ("delay_change", C.c_int32), ("wrapper_known_delay", C.c_int32),
+        ("farend_old", (C.c_int16 * 80) * 2), ("far_fifo", Fifo), ("far_ring", C.c_int16 * 4000),
+        ("frm_far_fifo", Fifo), ("frm_near_fifo", Fifo), ("frm_clean_fifo", Fifo), ("frm_out_fifo", Fifo),
+        ("frm_far", C.c_int16 * 144), ("frm_near", C.c_int16 * 144), ("frm_clean", C.c_int16 * 144),
+        ("frm_out", C.c_int16 * 144),
+        ("mult", C.c_int16), ("cng_mode", C.c_int16), ("seed", C.c_uint32), ("tot_count", C.c_uint32),
+        ("first_vad", C.c_int32), ("q_clean", C.c_int16), ("q_clean_old", C.c_int16), ("q_noisy", C.c_int16),
+        ("q_noisy_old", C.c_int16), ("x_buf", C.c_int16 * 128), ("d_noisy", C.c_int16 * 128),
+        ("d_clean", C.c_int16 * 128), ("out_ola", C.c_int16 * 64), ("ch_stored", C.c_int16 * 65),
+        ("ch_adapt16", C.c_int16 * 65), ("ch_adapt32", C.c_int32 * 65), ("echo_filt", C.c_int32 * 65),
+        ("near_filt", C.c_int16 * 65), ("noise_est", C.c_int32 * 65), ("noise_low_ctr", C.c_int32 * 65),
+        ("noise_high_ctr", C.c_int32 * 65), ("noise_est_ctr", C.c_int16), ("near_log", C.c_int16 * 64),
+        ("echo_adapt_log", C.c_int16 * 64), ("echo_stored_log", C.c_int16 * 64), ("far_log", C.c_int16),
+        ("mse_adapt_old", C.c_int32), ("mse_stored_old", C.c_int32), ("mse_threshold", C.c_int32),
+        ("far_e_min", C.c_int16), ("far_e_max", C.c_int16), ("far_e_maxmin", C.c_int16), ("far_e_vad", C.c_int16),
+        ("far_e_mse", C.c_int16), ("current_vad", C.c_int32), ("vad_update_count", C.c_int16),
+        ("startup_state", C.c_int16), ("mse_channel_count", C.c_int16), ("sup_gain", C.c_int16),
+        ("sup_gain_old", C.c_int16), ("sup_a", C.c_int16), ("sup_d", C.c_int16), ("sup_diff_ab", C.c_int16),
+        ("sup_diff_bd", C.c_int16), ("far_hist", C.c_uint16 * 6500), ("far_hist_pos", C.c_int32),
+        ("far_hist_q", C.c_int32 * 100), ("thr_far", C.c_int32 * 65), ("thr_near", C.c_int32 * 65),
+        ("thr_far_init", C.c_int32), ("thr_near_init", C.c_int32), ("bin_far", C.c_uint32 * 100),
+        ("bin_far_head", C.c_int32), ("mean_bit_counts", C.c_int32 * 100), ("minimum_probability", C.c_int32),
+        ("last_delay_probability", C.c_int32), ("last_delay", C.c_int32)]
+
+
+class OracleInstance:
+    """One oracle instance driven call by call (the reference protocol of main.cc:111-144)."""
+
+    def __init__(self, fs=16000, cng_mode=1, echo_mode=3):
+        self.lib = oracle()
+        assert self.lib.oracle_aecm_sizeof() == C.sizeof(OracleState), "OracleState mirror out of date"
+        self.h = self.lib.oracle_aecm_create()
+        self.rc_init = self.lib.oracle_aecm_init(self.h, fs)
+        self.rc_cfg = self.lib.oracle_aecm_set_config(self.h, cng_mode, echo_mode)
+
+    def buffer_farend(self, far):
+        far = np.ascontiguousarray(far, dtype=np.int16)
+        return self.lib.oracle_aecm_buffer_farend(self.h, _ptr(far), far.size)
+
+    def process(self, near, clean=None, ms=40):
+        near = np.ascontiguousarray(near, dtype=np.int16)
+        out = np.zeros_like(near)
+        if clean is not None:
+            clean = np.ascontiguousarray(clean, dtype=np.int16)
+        rc = self.lib.oracle_aecm_process(self.h, _ptr(near), _ptr(clean), _ptr(out), near.size, int(ms))
+        return rc, out
+
+    def state(self) -> OracleState:
+        return OracleState.from_address(self.h)
+
+    def close(self):
+        if self.h:
+            self.lib.oracle_aecm_free(self.h)
+            self.h = None
+
+
+def compare_states(dev, orc: OracleState, use_clean=False):
+    """Field-by-field comparison of a device ``InstanceState`` with an ``OracleState``.
+    Returns a list of human-readable mismatch descriptions (empty = identical live state)."""
+    bad = []
+
+    def arr(x, n=None):
+        a = np.ctypeslib.as_array(x)
+        return a if n is None else a[:n]
+
+    def chk(name, d, o):
+        d = np.asarray(d).astype(np.int64).ravel()
+        o = np.asarray(o).astype(np.int64).ravel()
+        if d.shape != o.shape or (d != o).any():
+            idx = np.nonzero(d != o)[0][:4] if d.shape == o.shape else []
+            bad.append(f"{name}: dev{d[idx].tolist() if len(idx) else d[:4].tolist()} "
+                       f"oracle{o[idx].tolist() if len(idx) else o[:4].tolist()} at {list(idx)}")
+
+    S = dev.s
+    for f in ("ch_adapt32", "echo_filt", "noise_est", "ch_stored", "ch_adapt16", "near_filt", "noise_low_ctr",
+              "noise_high_ctr"):
+        chk(f, arr(getattr(dev, f), 65), arr(getattr(orc, f)))
+    chk("x_old", arr(dev.x_old), arr(orc.x_buf)[:64])
+    chk("d_noisy_old", arr(dev.d_noisy_old), arr(orc.d_noisy)[:64])
+    if use_clean:
+        chk("d_clean_old", arr(dev.d_clean_old), arr(orc.d_clean)[:64])
+    chk("out_ola", arr(dev.out_ola), arr(orc.out_ola))
+    chk("thr_far", arr(dev.thr_far), arr(orc.thr_far)[12:44])
+    chk("thr_near", arr(dev.thr_near), arr(orc.thr_near)[12:44])
+    dh, oh = S.bin_far_head, orc.bin_far_head
+    chk("bin_far(by delay)", np.roll(arr(dev.bin_far, 100), -dh), np.roll(arr(orc.bin_far), -oh))
+    chk("mean_bit_counts", arr(dev.mean_bit_counts, 100), arr(orc.mean_bit_counts))
+    k = (S.log_head + np.arange(20)) & 31
+    for f in ("near_log", "echo_adapt_log", "echo_stored_log"):
+        chk(f, arr(getattr(dev, f))[k], arr(getattr(orc, f))[:20])
+    # FIFOs: compare live contents
+    def live(store, rd, cnt, cap):
+        return np.asarray(store)[(rd + np.arange(cnt)) % cap]
+    chk("frm_in_cnt", S.frm_in_cnt, orc.frm_far_fifo.cnt)
+    chk("frm_far live", live(arr(dev.frm_far), S.frm_in_rd, S.frm_in_cnt, 144),
+        live(arr(orc.frm_far), orc.frm_far_fifo.rd, orc.frm_far_fifo.cnt, 144))
+    chk("frm_near live", live(arr(dev.frm_near), S.frm_in_rd, S.frm_in_cnt, 144),
+        live(arr(orc.frm_near), orc.frm_near_fifo.rd, orc.frm_near_fifo.cnt, 144))
+    chk("frm_out_cnt", S.frm_out_cnt, orc.frm_out_fifo.cnt)
+    chk("frm_out live", live(arr(dev.frm_out), S.frm_out_rd, S.frm_out_cnt, 144),
+        live(arr(orc.frm_out), orc.frm_out_fifo.rd, orc.frm_out_fifo.cnt, 144))
+    chk("farend_old", arr(dev.farend_old), arr(orc.farend_old))
+    chk("far_cnt", S.far_cnt, orc.far_fifo.cnt)
+    chk("far_rd", S.far_rd, orc.far_fifo.rd)
+    for f in ("mult", "cng_mode", "seed", "tot_count", "first_vad", "q_clean", "q_clean_old", "q_noisy", "q_noisy_old",
+              "noise_est_ctr", "far_log", "mse_adapt_old", "mse_stored_old", "mse_threshold", "far_e_min", "far_e_max",
+              "far_e_maxmin", "far_e_vad", "far_e_mse", "current_vad", "vad_update_count", "startup_state",
+              "mse_channel_count", "sup_gain", "sup_gain_old", "sup_a", "sup_d", "sup_diff_ab", "sup_diff_bd",
+              "far_hist_pos", "thr_far_init", "thr_near_init", "minimum_probability", "last_delay_probability",
+              "last_delay", "fs", "init_flag", "echo_mode", "buf_size_start", "counter", "sum", "first_val",
+              "check_buf_size_ctr", "ms_in_snd_card_buf", "ec_startup", "check_buff_size", "filt_delay",
+              "last_delay_diff", "time_for_delay_change", "delay_change", "wrapper_known_delay"):
+        chk(f, getattr(S, f), getattr(orc, f))
+    return bad

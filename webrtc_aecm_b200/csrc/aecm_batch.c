@@ -1,0 +1,356 @@
+/*
+ * aecm_batch.c -- host side (plain C) of the batched AECM engine: device arenas, streams, argument
+ * validation and host<->device staging around the CUDA launchers of aecm_kernels.cu.  There is no CPU
+ * implementation of the algorithm here: if CUDA is unavailable every entry point fails loudly.
+ */
+#include "aecm_b200.h"
+
+#include <cuda_runtime_api.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include "aecm_state.h"
+
+struct AecmB200Batch {
+    int32_t n, device;
+    AecmBatchPlanes planes;
+    cudaStream_t stream;
+    int owns_stream;
+    /* device staging for the host-plane calls, grown on demand */
+    int16_t *d_far, *d_near, *d_clean, *d_out;
+    size_t d_plane_samples;
+    int16_t *d_ms;
+    uint8_t *d_mask;
+    size_t d_mask_bytes;
+    int32_t *d_status;
+    int16_t *d_path;
+    char err[256];
+};
+
+static int fail(AecmB200Batch *b, const char *what, cudaError_t e) {
+    if (b) snprintf(b->err, sizeof(b->err), "%s: %s", what, cudaGetErrorString(e));
+    return AECM_UNSPECIFIED_ERROR;
+}
+#define CU(b, call)                                         \
+    do {                                                    \
+        cudaError_t e_ = (call);                            \
+        if (e_ != cudaSuccess) return fail((b), #call, e_); \
+    } while (0)
+
+int32_t AecmB200_DeviceCount(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+    return n;
+}
+
+AecmB200Batch *AecmB200_Create(int32_t n, int32_t device) {
+    AecmB200Batch *b;
+    if (n <= 0) return NULL;
+    if (cudaSetDevice(device) != cudaSuccess) {
+        fprintf(stderr, "aecm_b200: CUDA device %d unavailable (%s); this library has no CPU path\n", device,
+                cudaGetErrorString(cudaGetLastError()));
+        return NULL;
+    }
+    b = (AecmB200Batch *)calloc(1, sizeof(*b));
+    if (!b) return NULL;
+    b->n = n;
+    b->device = device;
+    b->planes.n_instances = n;
+    if (cudaMalloc((void **)&b->planes.state, (size_t)n * sizeof(AecmInstanceState)) != cudaSuccess ||
+        cudaMalloc((void **)&b->planes.far_hist, (size_t)n * AECM_MAX_DELAY * AECM_HIST_ROW * sizeof(uint16_t)) != cudaSuccess ||
+        cudaMalloc((void **)&b->planes.far_ring, (size_t)n * AECM_FAR_RING * sizeof(int16_t)) != cudaSuccess ||
+        cudaMalloc((void **)&b->d_ms, (size_t)n * sizeof(int16_t)) != cudaSuccess ||
+        cudaMalloc((void **)&b->d_status, (size_t)n * sizeof(int32_t)) != cudaSuccess ||
+        cudaMalloc((void **)&b->d_path, AECM_BINS * sizeof(int16_t)) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&b->stream, cudaStreamNonBlocking) != cudaSuccess) {
+        fprintf(stderr, "aecm_b200: device allocation failed: %s\n", cudaGetErrorString(cudaGetLastError()));
+        AecmB200_Free(b);
+        return NULL;
+    }
+    b->owns_stream = 1;
+    /* calloc semantics of the reference's Create: an un-Init'ed instance reports AECM_UNINITIALIZED_ERROR */
+    if (cudaMemsetAsync(b->planes.state, 0, (size_t)n * sizeof(AecmInstanceState), b->stream) != cudaSuccess ||
+        cudaStreamSynchronize(b->stream) != cudaSuccess) {
+        AecmB200_Free(b);
+        return NULL;
+    }
+    return b;
+}
+
+void AecmB200_Free(AecmB200Batch *b) {
+    if (!b) return;
+    cudaSetDevice(b->device);
+    if (b->stream) cudaStreamSynchronize(b->stream);
+    cudaFree(b->planes.state);
+    cudaFree(b->planes.far_hist);
+    cudaFree(b->planes.far_ring);
+    cudaFree(b->d_far);
+    cudaFree(b->d_near);
+    cudaFree(b->d_clean);
+    cudaFree(b->d_out);
+    cudaFree(b->d_ms);
+    cudaFree(b->d_mask);
+    cudaFree(b->d_status);
+    cudaFree(b->d_path);
+    if (b->stream && b->owns_stream) cudaStreamDestroy(b->stream);
+    free(b);
+}
+
+int32_t AecmB200_NumInstances(const AecmB200Batch *b) { return b ? b->n : -1; }
+int32_t AecmB200_Device(const AecmB200Batch *b) { return b ? b->device : -1; }
+const char *AecmB200_LastError(const AecmB200Batch *b) { return b ? b->err : "null batch"; }
+void *AecmB200_CudaStream(const AecmB200Batch *b) { return b ? (void *)b->stream : NULL; }
+
+int32_t AecmB200_AdoptCudaStream(AecmB200Batch *b, void *s) {
+    if (!b) return -1;
+    CU(b, cudaSetDevice(b->device));
+    CU(b, cudaStreamSynchronize(b->stream));
+    if (b->owns_stream) cudaStreamDestroy(b->stream);
+    b->stream = (cudaStream_t)s;
+    b->owns_stream = 0;
+    return 0;
+}
+
+int32_t AecmB200_Synchronize(AecmB200Batch *b) {
+    if (!b) return -1;
+    CU(b, cudaSetDevice(b->device));
+    CU(b, cudaStreamSynchronize(b->stream));
+    return 0;
+}
+
+void *AecmB200_HostAlloc(size_t bytes) {
+    void *p = NULL;
+    if (cudaMallocHost(&p, bytes) != cudaSuccess) return NULL;
+    return p;
+}
+void AecmB200_HostFree(void *p) {
+    if (p) cudaFreeHost(p);
+}
+
+size_t AecmB200_StateBytes(void) { return sizeof(AecmInstanceState); }
+int64_t AecmB200_KernelLaunchCount(void) { return aecm_cuda_kernel_launch_count(); }
+
+static int range_ok(const AecmB200Batch *b, int32_t first, int32_t count) {
+    return first >= 0 && count >= 0 && (int64_t)first + count <= b->n;
+}
+
+int32_t AecmB200_ReadState(AecmB200Batch *b, int32_t instance, void *dst, size_t bytes) {
+    if (!b) return -1;
+    if (!dst) return AECM_NULL_POINTER_ERROR;
+    if (!range_ok(b, instance, 1) || bytes > sizeof(AecmInstanceState)) return AECM_BAD_PARAMETER_ERROR;
+    CU(b, cudaSetDevice(b->device));
+    CU(b, cudaMemcpyAsync(dst, b->planes.state + instance, bytes, cudaMemcpyDeviceToHost, b->stream));
+    CU(b, cudaStreamSynchronize(b->stream));
+    return 0;
+}
+
+int32_t AecmB200_Reset(AecmB200Batch *b, int32_t first, int32_t count) {
+    if (!b) return -1;
+    if (!range_ok(b, first, count)) return AECM_BAD_PARAMETER_ERROR;
+    CU(b, cudaSetDevice(b->device));
+    CU(b, cudaMemsetAsync(b->planes.state + first, 0, (size_t)count * sizeof(AecmInstanceState), b->stream));
+    CU(b, cudaStreamSynchronize(b->stream));
+    return 0;
+}
+
+int32_t AecmB200_Init(AecmB200Batch *b, int32_t first, int32_t count, int32_t fs) {
+    if (!b) return -1;
+    if (fs != 8000 && fs != 16000) return AECM_BAD_PARAMETER_ERROR; /* echo_control_mobile.cc:150-152 */
+    if (!range_ok(b, first, count)) return AECM_BAD_PARAMETER_ERROR;
+    CU(b, cudaSetDevice(b->device));
+    CU(b, (cudaError_t)aecm_cuda_launch_init(&b->planes, first, count, fs, b->stream));
+    return 0;
+}
+
+static int copy_status_out(AecmB200Batch *b, int32_t *status, int32_t count) {
+    if (status) CU(b, cudaMemcpyAsync(status, b->d_status, (size_t)count * sizeof(int32_t), cudaMemcpyDeviceToHost, b->stream));
+    CU(b, cudaStreamSynchronize(b->stream));
+    return 0;
+}
+
+int32_t AecmB200_SetConfig(AecmB200Batch *b, int32_t first, int32_t count, AecmConfig cfg, int32_t *status) {
+    if (!b) return -1;
+    if (!range_ok(b, first, count)) return AECM_BAD_PARAMETER_ERROR;
+    CU(b, cudaSetDevice(b->device));
+    CU(b, (cudaError_t)aecm_cuda_launch_set_config(&b->planes, first, count, cfg.cngMode, cfg.echoMode, b->d_status, b->stream));
+    return copy_status_out(b, status, count);
+}
+
+size_t WebRtcAecm_echo_path_size_bytes(void) { return AECM_BINS * sizeof(int16_t); } /* echo_control_mobile.cc:530-532 */
+
+int32_t AecmB200_InitEchoPath(AecmB200Batch *b, int32_t instance, const void *path, size_t size_bytes) {
+    int32_t st = 0, rc;
+    if (!b) return -1;
+    if (!path) return AECM_NULL_POINTER_ERROR;
+    if (size_bytes != WebRtcAecm_echo_path_size_bytes()) return AECM_BAD_PARAMETER_ERROR;
+    if (!range_ok(b, instance, 1)) return AECM_BAD_PARAMETER_ERROR;
+    CU(b, cudaSetDevice(b->device));
+    CU(b, cudaMemcpyAsync(b->d_path, path, size_bytes, cudaMemcpyHostToDevice, b->stream));
+    CU(b, (cudaError_t)aecm_cuda_launch_init_echo_path(&b->planes, instance, 1, b->d_path, AECM_BINS, b->d_status, b->stream));
+    rc = copy_status_out(b, &st, 1);
+    return rc ? rc : st;
+}
+
+int32_t AecmB200_GetEchoPath(AecmB200Batch *b, int32_t instance, void *path, size_t size_bytes) {
+    int32_t flag = 0;
+    const char *base;
+    if (!b) return -1;
+    if (!path) return AECM_NULL_POINTER_ERROR;
+    if (size_bytes != WebRtcAecm_echo_path_size_bytes()) return AECM_BAD_PARAMETER_ERROR;
+    if (!range_ok(b, instance, 1)) return AECM_BAD_PARAMETER_ERROR;
+    CU(b, cudaSetDevice(b->device));
+    base = (const char *)(b->planes.state + instance);
+    CU(b, cudaMemcpyAsync(&flag, base + offsetof(AecmInstanceState, s) + offsetof(AecmScalars, init_flag), sizeof(flag),
+                          cudaMemcpyDeviceToHost, b->stream));
+    CU(b, cudaStreamSynchronize(b->stream));
+    if (flag != AECM_INIT_MAGIC) return AECM_UNINITIALIZED_ERROR;
+    CU(b, cudaMemcpyAsync(path, base + offsetof(AecmInstanceState, ch_stored), size_bytes, cudaMemcpyDeviceToHost, b->stream));
+    CU(b, cudaStreamSynchronize(b->stream));
+    return 0;
+}
+
+static int32_t validate_stream_args(const AecmB200Batch *b, const AecmB200StreamArgs *a) {
+    if (!a) return AECM_NULL_POINTER_ERROR;
+    if (!a->farend && !a->nearendNoisy) return AECM_NULL_POINTER_ERROR;
+    if (a->nearendNoisy && !a->out) return AECM_NULL_POINTER_ERROR;            /* echo_control_mobile.cc:256-262 */
+    if (a->nrOfSamples != 80 && a->nrOfSamples != 160) return AECM_BAD_PARAMETER_ERROR; /* :209, :268 */
+    if (a->nCalls < 1 || !range_ok(b, a->first, a->count)) return AECM_BAD_PARAMETER_ERROR;
+    if (a->rowStride < (int64_t)a->nCalls * a->nrOfSamples) return AECM_BAD_PARAMETER_ERROR;
+    return 0;
+}
+
+static void fill_call_args(AecmCallArgs *k, const AecmB200StreamArgs *a) {
+    memset(k, 0, sizeof(*k));
+    k->far = a->farend;
+    k->near_noisy = a->nearendNoisy;
+    k->near_clean = a->nearendNoisy ? a->nearendClean : NULL;
+    k->out = a->out;
+    k->ms = a->msInSndCardBuf;
+    k->far_mask = a->farendMask;
+    k->status = a->status;
+    k->row_stride = a->rowStride;
+    k->first = a->first;
+    k->count = a->count;
+    k->samples_per_call = a->nrOfSamples;
+    k->n_calls = a->nCalls;
+    k->ms_uniform = a->msUniform;
+}
+
+int32_t AecmB200_ProcessStreamDevice(AecmB200Batch *b, const AecmB200StreamArgs *a) {
+    AecmCallArgs k;
+    int32_t rc;
+    if (!b) return -1;
+    rc = validate_stream_args(b, a);
+    if (rc) return rc;
+    if (a->count == 0) return 0;
+    CU(b, cudaSetDevice(b->device));
+    fill_call_args(&k, a);
+    CU(b, (cudaError_t)aecm_cuda_launch_call(&b->planes, &k, b->stream));
+    return 0;
+}
+
+static int grow_planes(AecmB200Batch *b, size_t samples, int need_clean) {
+    if (samples > b->d_plane_samples) {
+        cudaFree(b->d_far); cudaFree(b->d_near); cudaFree(b->d_clean); cudaFree(b->d_out);
+        b->d_far = b->d_near = b->d_clean = b->d_out = NULL;
+        b->d_plane_samples = 0;
+        CU(b, cudaMalloc((void **)&b->d_far, samples * sizeof(int16_t)));
+        CU(b, cudaMalloc((void **)&b->d_near, samples * sizeof(int16_t)));
+        CU(b, cudaMalloc((void **)&b->d_out, samples * sizeof(int16_t)));
+        b->d_plane_samples = samples;
+    }
+    if (need_clean && !b->d_clean) CU(b, cudaMalloc((void **)&b->d_clean, b->d_plane_samples * sizeof(int16_t)));
+    return 0;
+}
+
+int32_t AecmB200_ProcessStream(AecmB200Batch *b, const AecmB200StreamArgs *h) {
+    AecmB200StreamArgs d;
+    size_t width, rows, pitch_src, pitch_dst;
+    int32_t rc;
+    if (!b) return -1;
+    rc = validate_stream_args(b, h);
+    if (rc) return rc;
+    if (h->count == 0) return 0;
+    CU(b, cudaSetDevice(b->device));
+    width = (size_t)h->nCalls * (size_t)h->nrOfSamples; /* samples actually used per row */
+    rows = (size_t)h->count;
+    rc = grow_planes(b, rows * width, h->nearendClean != NULL);
+    if (rc) return rc;
+    pitch_src = (size_t)h->rowStride * sizeof(int16_t);
+    pitch_dst = width * sizeof(int16_t);
+    d = *h;
+    d.rowStride = (int64_t)width;
+    d.farend = d.nearendNoisy = d.nearendClean = NULL;
+    d.out = NULL;
+    if (h->farend) {
+        CU(b, cudaMemcpy2DAsync(b->d_far, pitch_dst, h->farend, pitch_src, pitch_dst, rows, cudaMemcpyHostToDevice, b->stream));
+        d.farend = b->d_far;
+    }
+    if (h->nearendNoisy) {
+        CU(b, cudaMemcpy2DAsync(b->d_near, pitch_dst, h->nearendNoisy, pitch_src, pitch_dst, rows, cudaMemcpyHostToDevice, b->stream));
+        d.nearendNoisy = b->d_near;
+        d.out = b->d_out;
+        if (h->nearendClean) {
+            CU(b, cudaMemcpy2DAsync(b->d_clean, pitch_dst, h->nearendClean, pitch_src, pitch_dst, rows, cudaMemcpyHostToDevice, b->stream));
+            d.nearendClean = b->d_clean;
+        }
+    }
+    if (h->msInSndCardBuf) {
+        CU(b, cudaMemcpyAsync(b->d_ms, h->msInSndCardBuf, rows * sizeof(int16_t), cudaMemcpyHostToDevice, b->stream));
+        d.msInSndCardBuf = b->d_ms;
+    }
+    if (h->farendMask) {
+        const size_t mb = rows * (size_t)h->nCalls;
+        if (mb > b->d_mask_bytes) {
+            cudaFree(b->d_mask);
+            b->d_mask = NULL;
+            b->d_mask_bytes = 0;
+            CU(b, cudaMalloc((void **)&b->d_mask, mb));
+            b->d_mask_bytes = mb;
+        }
+        CU(b, cudaMemcpyAsync(b->d_mask, h->farendMask, mb, cudaMemcpyHostToDevice, b->stream));
+        d.farendMask = b->d_mask;
+    }
+    d.status = b->d_status;
+    rc = AecmB200_ProcessStreamDevice(b, &d);
+    if (rc) return rc;
+    if (h->nearendNoisy)
+        CU(b, cudaMemcpy2DAsync(h->out, pitch_src, b->d_out, pitch_dst, pitch_dst, rows, cudaMemcpyDeviceToHost, b->stream));
+    return copy_status_out(b, h->status, h->count);
+}
+
+int32_t AecmB200_BufferFarend(AecmB200Batch *b, const int16_t *farend, size_t n, int32_t *status) {
+    AecmB200StreamArgs a;
+    if (!b) return -1;
+    if (!farend) return AECM_NULL_POINTER_ERROR; /* echo_control_mobile.cc:203 */
+    memset(&a, 0, sizeof(a));
+    a.farend = farend;
+    a.rowStride = (int64_t)n;
+    a.count = b->n;
+    a.nrOfSamples = (int32_t)n;
+    a.nCalls = 1;
+    a.status = status;
+    if (n != 80 && n != 160) return AECM_BAD_PARAMETER_ERROR;
+    return AecmB200_ProcessStream(b, &a);
+}
+
+int32_t AecmB200_Process(AecmB200Batch *b, const int16_t *near_noisy, const int16_t *near_clean, int16_t *out, size_t n,
+                         const int16_t *ms, int16_t ms_uniform, int32_t *status) {
+    AecmB200StreamArgs a;
+    if (!b) return -1;
+    if (!near_noisy || !out) return AECM_NULL_POINTER_ERROR; /* echo_control_mobile.cc:256-262 */
+    if (n != 80 && n != 160) return AECM_BAD_PARAMETER_ERROR;
+    memset(&a, 0, sizeof(a));
+    a.nearendNoisy = near_noisy;
+    a.nearendClean = near_clean;
+    a.out = out;
+    a.rowStride = (int64_t)n;
+    a.count = b->n;
+    a.nrOfSamples = (int32_t)n;
+    a.nCalls = 1;
+    a.msInSndCardBuf = ms;
+    a.msUniform = ms_uniform;
+    a.status = status;
+    return AecmB200_ProcessStream(b, &a);
+}

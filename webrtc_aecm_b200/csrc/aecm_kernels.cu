@@ -1,0 +1,1189 @@
+// aecm_kernels.cu -- the batched AECM engine's device code for sm_100a.
+//
+// One warp owns one AECM instance.  A launch stages the instance record (aecm_state.h) from HBM into
+// shared memory with 128-bit coalesced accesses, runs `n_calls` fused 10 ms API calls
+// (BufferFarend + Process: far-end jitter FIFO -> 80-sample frames -> 64-sample blocks -> block DSP) and
+// writes the record back.  All arithmetic is int16/int32 Q-format and bit-exact with the reference's
+// generic C path; every stage cites the reference lines (relative to /root/reference/aecm) it implements.
+//
+// Lane mapping: 65 frequency bins -> bins lane, lane+32 and (lane 0 only) bin 64; 128 time samples ->
+// 4 per lane; the 32 delay-estimator bands -> one per lane (so __ballot_sync *is* the binary spectrum);
+// 100 delay candidates -> 4 strided passes.  Scalar state-machine code runs redundantly on all lanes on
+// the shared-memory copy (every lane writes the same value), which avoids broadcasts.
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "aecm_state.h"
+#include "aecm_tables.h"
+
+namespace {
+
+constexpr unsigned kFull = 0xffffffffu;
+constexpr int kWarpsPerCta = 4;
+
+// ---- algorithm constants, aecm_defines.h:28-85 ----
+constexpr int kConvLen = 512;
+constexpr int kFarEnergyMin = 1025;
+constexpr int kFarEnergyDiff = 929;
+constexpr int kEnergyDevTol = 400;
+constexpr int kFarEnergyVadRegion = 230;
+constexpr int kMuMin = 10, kMuMax = 1, kMuDiff = 9;
+constexpr int kMinMseCount = 20, kMinMseDiff = 29, kMseResolution = 5;
+constexpr int kResCh16 = 12, kResCh32 = 28, kChannelVad = 16, kResSupGain = 8;
+constexpr int kSupGainDefault = 256, kSupGainA = 3072, kSupGainB = 1536, kSupGainD = 256, kSupGainEpcDt = 200;
+constexpr int kOneQ14 = 16384, kNlpLow = 3277;
+
+// LCG jump-ahead: after k steps of seed' = (seed*69069 + 1) mod 2^31 the seed is mul[k-1]*seed + add[k-1]
+// (signal_processing_library.cc:129-136), so lane-parallel code can draw the k-th number directly.
+struct LcgTable {
+    uint32_t mul[64], add[64];
+};
+constexpr LcgTable make_lcg_table() {
+    LcgTable t{};
+    uint32_t a = 1, c = 0;
+    for (int k = 0; k < 64; k++) {
+        c = c * 69069u + 1u;
+        a = a * 69069u;
+        t.mul[k] = a & 0x7fffffffu;
+        t.add[k] = c & 0x7fffffffu;
+    }
+    return t;
+}
+__device__ const LcgTable kLcgJump = make_lcg_table();
+
+struct CtaTables {
+    uint32_t twiddle[64];
+    uint32_t cossin[360];
+    uint32_t lcg_mul[64], lcg_add[64];
+    int16_t hann[66];
+};
+
+struct __align__(16) WarpScratch {
+    uint32_t fft[128];     // packed complex int16: re in the low half, im in the high half
+    uint32_t dfw[68];      // near (or clean) spectrum after the sign flip of aecm_core_c.cc:188-190
+    int32_t echo_est[68];
+    uint16_t xfa[72], dfa_noisy[72], dfa_clean[72], far_row[72];
+    int16_t out_blk[64];
+};
+
+struct Ctx {
+    AecmInstanceState *st;  // shared-memory copy of the record
+    WarpScratch *sc;
+    const CtaTables *tab;
+    uint16_t *far_hist;     // this instance's 100 x 66 rows in HBM
+    int16_t *far_ring;      // this instance's 4000-sample jitter FIFO in HBM
+    int lane;
+};
+
+// ------------------------------------------------------------------------------------------------
+// scalar primitives (spl_inl.h, signal_processing_library.{h,cc})
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ int s16(int v) { return (int)(short)v; }  // int16 truncation + sign extension
+__device__ __forceinline__ int norm_w32(int a) { return a == 0 ? 0 : __clz(a < 0 ? ~a : a) - 1; }   // spl_inl.h:96
+__device__ __forceinline__ int norm_u32(unsigned a) { return a == 0 ? 0 : __clz((int)a); }          // spl_inl.h:101
+__device__ __forceinline__ int norm_w16(int a) { return a == 0 ? 0 : __clz(a < 0 ? ~a : a) - 17; } // spl_inl.h:107
+__device__ __forceinline__ int add_sat32(int a, int b) {  // spl_inl.h:70-82
+    int r;
+    asm("add.sat.s32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b));
+    return r;
+}
+__device__ __forceinline__ int sat16(int v) { return max(-32768, min(32767, v)); }  // spl_inl.h:59-68
+__device__ __forceinline__ uint32_t pack16(int lo, int hi) { return __byte_perm((uint32_t)lo, (uint32_t)hi, 0x5410); }
+__device__ __forceinline__ int lo16(uint32_t v) { return (int)(short)(v & 0xffffu); }
+__device__ __forceinline__ int hi16(uint32_t v) { return ((int)v) >> 16; }
+
+// WEBRTC_SPL_SHIFT_W32 (signal_processing_library.h:130).  The shift count of the NLMS rescaling
+// (aecm_core.cc:906-912) can leave [-31, 31]; the reference then executes an x86 SAR/SHL, which uses the
+// count modulo 32, so counts are masked here the same way (CUDA's native shifts clamp instead).
+__device__ __forceinline__ int shift_s32(int x, int c) {
+    return c >= 0 ? (int)((uint32_t)x << (c & 31)) : x >> ((-c) & 31);
+}
+__device__ __forceinline__ uint32_t shift_u32(uint32_t x, int c) { return c >= 0 ? x << (c & 31) : x >> ((-c) & 31); }
+
+// signal_processing_library.cc:84-105 is floor(sqrt(v)) for v in [0, 2^31)
+__device__ __forceinline__ int sqrt_floor(int v) {
+    uint32_t r = (uint32_t)__float2int_rz(sqrtf((float)v));
+    if (r * r > (uint32_t)v) r--;
+    if ((r + 1) * (r + 1) <= (uint32_t)v) r++;
+    return (int)r;
+}
+
+__device__ __forceinline__ void mean_estimator_fix(int v, int factor, int &mean) {  // delay_estimator.cc:690-702
+    int d = v - mean;
+    d = d < 0 ? -((-d) >> factor) : d >> factor;
+    mean += d;
+}
+
+__device__ __forceinline__ int log_energy_q8(uint32_t e, int q) {  // aecm_core.cc:612-628
+    int r = 7 << 7;
+    if (e > 0) {
+        const int z = __clz((int)e);
+        const int frac = (int)(((e << z) & 0x7fffffffu) >> 23);
+        r = s16(r + ((31 - z) << 8) + frac - (q << 8));
+    }
+    return r;
+}
+
+__device__ __forceinline__ int asym_filt(int old_v, int in, int step_pos, int step_neg) {  // aecm_core.cc:588-605
+    if (old_v == 32767 || old_v == -32768) return in;
+    return old_v > in ? s16(old_v - ((old_v - in) >> step_neg)) : s16(old_v + ((in - old_v) >> step_pos));
+}
+
+__device__ __forceinline__ int wrap_add(int base, int k, int cap) {  // (base + k) mod cap for 0 <= base,k < cap
+    const int v = base + k;
+    return v >= cap ? v - cap : v;
+}
+__device__ __forceinline__ int brev7(int n) { return (int)(__brev((unsigned)n) >> 25); }
+
+// ------------------------------------------------------------------------------------------------
+// 128-point fixed-point complex FFT / IFFT on a warp (complex_fft.c:241-491, mode 1)
+// Data lives in shared memory as 128 packed words in bit-reversed input order; stage s pairs words that
+// differ in bit s; each lane executes two butterflies per stage.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void fft128_forward(uint32_t *buf, const uint32_t *tw, int lane) {
+#pragma unroll
+    for (int s = 0; s < 7; s++) {
+        const int half = 1 << s;
+#pragma unroll
+        for (int h = 0; h < 2; h++) {
+            const int b = lane + 32 * h;
+            const int m = b & (half - 1);
+            const int i = ((b >> s) << (s + 1)) | m;
+            const int j = i + half;
+            const uint32_t w = tw[m << (6 - s)];
+            const int wr = lo16(w), wi = -hi16(w);  // complex_fft.c:303-304
+            const uint32_t cj = buf[j], ci = buf[i];
+            const int xr = lo16(cj), xi = hi16(cj);
+            const int tr = (wr * xr - wi * xi + 1) >> 1;  // :332-338
+            const int ti = (wr * xi + wi * xr + 1) >> 1;
+            const int qr = lo16(ci) * 16384 + 16384;      // :340-341 plus CFFTRND2
+            const int qi = hi16(ci) * 16384 + 16384;
+            buf[j] = pack16((qr - tr) >> 15, (qi - ti) >> 15);  // :343-350
+            buf[i] = pack16((qr + tr) >> 15, (qi + ti) >> 15);
+        }
+        __syncwarp();
+    }
+}
+
+// returns the accumulated scale (complex_fft.c:381-396: shift 0/1/2 per stage from the pre-stage peak)
+__device__ __forceinline__ int fft128_inverse(uint32_t *buf, const uint32_t *tw, int lane, int peak) {
+    int scale = 0;
+#pragma unroll
+    for (int s = 0; s < 7; s++) {
+        const int half = 1 << s;
+        const int shift = (peak > 13573) + (peak > 27146);
+        const int rnd = 8192 << shift;
+        scale += shift;
+        int mx = 0;
+#pragma unroll
+        for (int h = 0; h < 2; h++) {
+            const int b = lane + 32 * h;
+            const int m = b & (half - 1);
+            const int i = ((b >> s) << (s + 1)) | m;
+            const int j = i + half;
+            const uint32_t w = tw[m << (6 - s)];
+            const int wr = lo16(w), wi = hi16(w);  // complex_fft.c:437-438
+            const uint32_t cj = buf[j], ci = buf[i];
+            const int xr = lo16(cj), xi = hi16(cj);
+            const int tr = (wr * xr - wi * xi + 1) >> 1;  // :465-470
+            const int ti = (wr * xi + wi * xr + 1) >> 1;
+            const int qr = lo16(ci) * 16384 + rnd;        // :472-473 plus round2
+            const int qi = hi16(ci) * 16384 + rnd;
+            const int sh = shift + 14;
+            const int ar = s16((qr - tr) >> sh), ai = s16((qi - ti) >> sh);  // :475-482
+            const int br = s16((qr + tr) >> sh), bi = s16((qi + ti) >> sh);
+            buf[j] = pack16(ar, ai);
+            buf[i] = pack16(br, bi);
+            mx = max(max(max(abs(ar), abs(ai)), max(abs(br), abs(bi))), mx);
+        }
+        peak = min(__reduce_max_sync(kFull, mx), 32767);  // WebRtcSpl_MaxAbsValueW16 of the next stage's input
+        __syncwarp();
+    }
+    return scale;
+}
+
+// ------------------------------------------------------------------------------------------------
+// TimeToFrequencyDomain (aecm_core_c.cc:261-365) incl. WindowAndFFT (:166-191)
+// old64: previous block half in shared memory; NewAt(k): k-th new sample.  Writes 65 magnitudes, optionally
+// the packed complex bins, returns the dynamic-Q shift; *sum_out = sum of magnitudes.
+// ------------------------------------------------------------------------------------------------
+template <class NewAt>
+__device__ __forceinline__ int time_to_frequency(const Ctx &c, const int16_t *old64, NewAt new_at, uint16_t *mag_out,
+                                                 uint32_t *cplx_out, uint32_t &sum_out) {
+    const int lane = c.lane;
+    uint32_t *buf = c.sc->fft;
+    int x[4];
+    x[0] = old64[lane];
+    x[1] = old64[lane + 32];
+    x[2] = new_at(lane);
+    x[3] = new_at(lane + 32);
+    int peak = max(max(abs(x[0]), abs(x[1])), max(abs(x[2]), abs(x[3])));
+    peak = min(__reduce_max_sync(kFull, peak), 32767);  // signal_processing_library.cc:154-174
+    const int q = norm_w16(peak);                       // :288-289
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        const int n = lane + 32 * k;
+        const int scaled = s16(x[k] << q);              // :177 / :179
+        const int w = c.tab->hann[n < 64 ? n : 128 - n];
+        buf[brev7(n)] = (uint32_t)(((scaled * w) >> 14) & 0xffff);  // :178 / :180-181, imaginary part 0
+    }
+    __syncwarp();
+    fft128_forward(buf, c.tab->twiddle, lane);
+    uint32_t sum = 0;
+#pragma unroll
+    for (int p = 0; p < 3; p++) {
+        const int i = lane + 32 * p;
+        if (i < AECM_BINS) {
+            const uint32_t v = buf[i];
+            const int re = lo16(v);
+            const int im = (i == 0 || i == 64) ? 0 : s16(-hi16(v));  // :188-190, :296-297
+            int mag;
+            if (re == 0) mag = abs(im);       // :305-308; |-32768| = 32768 as uint16
+            else if (im == 0) mag = abs(re);
+            else {
+                const uint32_t e = (uint32_t)(re * re) + (uint32_t)(im * im);  // :350-354 with AddSatW32
+                mag = sqrt_floor((int)min(e, 0x7fffffffu));
+            }
+            mag_out[i] = (uint16_t)mag;
+            if (cplx_out) cplx_out[i] = pack16(re, im);
+            sum += (uint32_t)mag;
+        }
+    }
+    sum_out = __reduce_add_sync(kFull, sum);
+    __syncwarp();
+    return q;
+}
+
+// ------------------------------------------------------------------------------------------------
+// binary spectrum of bands 12..43 (delay_estimator_wrapper.cc:92-125): lane l <-> band 12+l <-> bit l
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t binary_spectrum(const uint16_t *spec, int32_t *thr, int q, int32_t &initialized,
+                                                    int lane) {
+    const int sp = spec[12 + lane];
+    const int s15 = (int)((uint32_t)sp << (15 - q));
+    int t = thr[lane];
+    if (!initialized) {  // warp-uniform
+        const unsigned any = __ballot_sync(kFull, sp > 0);
+        if (sp > 0) t = s15 >> 1;
+        if (any) initialized = 1;
+    }
+    mean_estimator_fix(s15, 6, t);
+    thr[lane] = t;
+    return __ballot_sync(kFull, s15 > t);
+}
+
+// WebRtc_ProcessBinarySpectrum (delay_estimator.cc:521-664) with robust validation off, lookahead 0.
+__device__ __forceinline__ int process_binary_spectrum(AecmInstanceState *st, uint32_t near_bits, int lane) {
+    AecmScalars &S = st->s;
+    const int head = S.bin_far_head;
+    int key = 0x7fffffff, worst = 0, any_far = 0;
+#pragma unroll
+    for (int p = 0; p < 4; p++) {
+        const int d = lane + 32 * p;
+        if (d < AECM_MAX_DELAY) {
+            const uint32_t fw = st->bin_far[wrap_add(head, d, AECM_MAX_DELAY)];
+            const int fbits = __popc(fw);
+            int mean = st->mean_bit_counts[d];
+            if (fbits > 0) {  // :550-564
+                mean_estimator_fix(__popc(near_bits ^ fw) << 9, 13 - ((3 * fbits) >> 4), mean);
+                st->mean_bit_counts[d] = mean;
+                any_far = 1;
+            }
+            key = min(key, (mean << 7) | d);  // value-major, index-minor: first index wins ties (:568-572)
+            worst = max(worst, mean);
+        }
+    }
+    key = __reduce_min_sync(kFull, key);
+    worst = __reduce_max_sync(kFull, worst);
+    any_far = __any_sync(kFull, any_far);  // :623-626
+    const int best = min(key >> 7, 32 << 9);
+    const int cand = key & 127;
+    const int depth = worst - best;
+    if (S.minimum_probability > 8704 && depth > 2816) {  // :593-605
+        const int thr = max(best + 1024, 8704);
+        if (S.minimum_probability > thr) S.minimum_probability = thr;
+    }
+    S.last_delay_probability++;  // :608
+    const bool valid = depth > 1024 && (best < S.minimum_probability || best < S.last_delay_probability);
+    if (any_far && valid) {  // :643-661
+        S.last_delay = cand;
+        if (best < S.last_delay_probability) S.last_delay_probability = best;
+    }
+    return S.last_delay;
+}
+
+// ------------------------------------------------------------------------------------------------
+// one 64-sample block (aecm_core_c.cc:368-711).  Input samples are read from the frame FIFOs in shared
+// memory starting at in_rd / clean_rd; the output block is left in sc->out_blk.
+// ------------------------------------------------------------------------------------------------
+__device__ __noinline__ void process_block(const Ctx &c, int in_rd, int clean_rd, bool use_clean) {
+    AecmInstanceState *st = c.st;
+    WarpScratch *sc = c.sc;
+    AecmScalars &S = st->s;
+    const int lane = c.lane;
+
+    if (S.startup_state < 2) S.startup_state = (S.tot_count >= kConvLen) + (S.tot_count >= 2 * kConvLen);  // :420-424
+
+    // ---- analysis: far, near (noisy) and optionally near (clean), :428-464 ----
+    uint32_t xfa_sum, dfa_noisy_sum, dfa_clean_sum;
+    const int far_q = time_to_frequency(
+        c, st->x_old, [&](int k) { return (int)st->frm_far[wrap_add(in_rd, k, AECM_FRM_RING)]; }, sc->xfa, nullptr, xfa_sum);
+    const int q_noisy = time_to_frequency(
+        c, st->d_noisy_old, [&](int k) { return (int)st->frm_near[wrap_add(in_rd, k, AECM_FRM_RING)]; }, sc->dfa_noisy,
+        sc->dfw, dfa_noisy_sum);
+    S.q_noisy_old = S.q_noisy;
+    S.q_noisy = q_noisy;
+    const uint16_t *dfa_clean = sc->dfa_noisy;
+    if (!use_clean) {
+        S.q_clean_old = S.q_noisy_old;
+        S.q_clean = S.q_noisy;
+    } else {
+        const int qc = time_to_frequency(
+            c, st->d_clean_old, [&](int k) { return (int)st->frm_clean[wrap_add(clean_rd, k, AECM_FRM_RING)]; },
+            sc->dfa_clean, sc->dfw, dfa_clean_sum);
+        S.q_clean_old = S.q_clean;
+        S.q_clean = qc;
+        dfa_clean = sc->dfa_clean;
+    }
+    const int q_clean = S.q_clean, q_clean_old = S.q_clean_old;
+
+    // ---- far magnitude history (aecm_core.cc:125-138): one 132-byte row to HBM ----
+    int pos = S.far_hist_pos + 1;
+    if (pos >= AECM_MAX_DELAY) pos = 0;
+    S.far_hist_pos = pos;
+    {
+        uint32_t *row = reinterpret_cast<uint32_t *>(c.far_hist + pos * AECM_HIST_ROW);
+        const uint32_t *src = reinterpret_cast<const uint32_t *>(sc->xfa);
+        row[lane] = src[lane];
+        if (lane == 0) row[32] = (uint32_t)sc->xfa[64] | ((uint32_t)far_q << 16);
+    }
+
+    // ---- delay estimation (delay_estimator_wrapper.cc:233-262, 447-476; delay_estimator.cc:369-382) ----
+    {
+        const uint32_t far_bits = binary_spectrum(sc->xfa, st->thr_far, far_q, S.thr_far_init, lane);
+        const int head = S.bin_far_head == 0 ? AECM_MAX_DELAY - 1 : S.bin_far_head - 1;
+        S.bin_far_head = head;
+        st->bin_far[head] = far_bits;
+    }
+    const uint32_t near_bits = binary_spectrum(sc->dfa_noisy, st->thr_near, q_noisy, S.thr_near_init, lane);
+    __syncwarp();
+    int delay = process_binary_spectrum(st, near_bits, lane);
+    if (delay == -2) delay = 0;  // aecm_core_c.cc:479-483
+
+    // ---- aligned far spectrum (aecm_core.cc:157-172) ----
+    const uint16_t *far_spec = sc->xfa;
+    int zx = far_q;
+    if (delay != 0) {
+        int rp = pos - delay;
+        if (rp < 0) rp += AECM_MAX_DELAY;
+        const uint32_t *row = reinterpret_cast<const uint32_t *>(c.far_hist + rp * AECM_HIST_ROW);
+        uint32_t *dst = reinterpret_cast<uint32_t *>(sc->far_row);
+        dst[lane] = row[lane];
+        const uint32_t tail = row[32];
+        if (lane == 0) dst[32] = tail;
+        zx = (int)(tail >> 16);
+        far_spec = sc->far_row;
+    }
+    __syncwarp();
+
+    // ---- CalcEnergies (aecm_core.cc:644-755) ----
+    const int lh = (S.log_head + AECM_LOG_RING - 1) & (AECM_LOG_RING - 1);
+    S.log_head = lh;
+    const int near_log0 = log_energy_q8(dfa_noisy_sum, q_noisy);
+    {
+        uint32_t e_far = 0, e_adapt = 0, e_stored = 0;
+#pragma unroll
+        for (int p = 0; p < 3; p++) {
+            const int i = lane + 32 * p;
+            if (i < AECM_BINS) {
+                const int f = far_spec[i];
+                const int est = (int)st->ch_stored[i] * f;  // aecm_core.cc:278-279
+                sc->echo_est[i] = est;
+                e_far += (uint32_t)f;
+                e_adapt += (uint32_t)((int)st->ch_adapt16[i] * f);
+                e_stored += (uint32_t)est;
+            }
+        }
+        e_far = __reduce_add_sync(kFull, e_far);
+        e_adapt = __reduce_add_sync(kFull, e_adapt);
+        e_stored = __reduce_add_sync(kFull, e_stored);
+        S.far_log = log_energy_q8(e_far, zx);
+        st->near_log[lh] = (int16_t)near_log0;
+        st->echo_adapt_log[lh] = (int16_t)log_energy_q8(e_adapt, kResCh16 + zx);
+        st->echo_stored_log[lh] = (int16_t)log_energy_q8(e_stored, kResCh16 + zx);
+    }
+    const int far_log = S.far_log;
+    if (far_log > kFarEnergyMin) {  // :692-730
+        int inc_max = 4, dec_max = 11, inc_min = 11, dec_min = 3;
+        if (S.startup_state == 0) { inc_max = 2; dec_min = 2; inc_min = 8; }
+        S.far_e_min = asym_filt(S.far_e_min, far_log, inc_min, dec_min);
+        S.far_e_max = asym_filt(S.far_e_max, far_log, inc_max, dec_max);
+        S.far_e_maxmin = s16(S.far_e_max - S.far_e_min);
+        int t16 = s16(2560 - S.far_e_min);
+        t16 = t16 > 0 ? s16((t16 * kFarEnergyVadRegion) >> 9) : 0;
+        t16 = s16(t16 + kFarEnergyVadRegion);
+        if ((S.startup_state == 0) | (S.vad_update_count > 1024)) {
+            S.far_e_vad = s16(S.far_e_min + t16);
+        } else if (S.far_e_vad > far_log) {
+            S.far_e_vad = s16(S.far_e_vad + ((far_log + t16 - S.far_e_vad) >> 6));
+            S.vad_update_count = 0;
+        } else {
+            S.vad_update_count = s16(S.vad_update_count + 1);
+        }
+        S.far_e_mse = s16(S.far_e_vad + (1 << 8));
+    }
+    if (far_log > S.far_e_vad) {  // :733-740
+        if ((S.startup_state == 0) | (S.far_e_maxmin > kFarEnergyDiff)) S.current_vad = 1;
+    } else {
+        S.current_vad = 0;
+    }
+    if (S.current_vad && S.first_vad) {  // :741-754
+        S.first_vad = 0;
+        __syncwarp();
+        if ((int)st->echo_adapt_log[lh] > near_log0) {
+#pragma unroll
+            for (int p = 0; p < 3; p++) {
+                const int i = lane + 32 * p;
+                if (i < AECM_BINS) st->ch_adapt16[i] = (int16_t)(st->ch_adapt16[i] >> 3);
+            }
+            __syncwarp();
+            st->echo_adapt_log[lh] = (int16_t)(st->echo_adapt_log[lh] - (3 << 8));
+            S.first_vad = 1;
+        }
+    }
+
+    // ---- CalcStepSize (aecm_core.cc:767-794) ----
+    int mu = kMuMax;
+    if (!S.current_vad) {
+        mu = 0;
+    } else if (S.startup_state > 0) {
+        if (S.far_e_min >= S.far_e_max) {
+            mu = kMuMin;
+        } else {
+            const int t16 = s16(far_log - S.far_e_min);
+            const int den = S.far_e_maxmin;
+            const int t32 = den != 0 ? (t16 * kMuDiff) / den : 0x7fffffff;
+            mu = s16(kMuMin - 1 - s16(t32));
+        }
+        if (mu < kMuMax) mu = kMuMax;
+    }
+    S.tot_count++;  // aecm_core_c.cc:506
+
+    // ---- UpdateChannel (aecm_core.cc:810-986) ----
+    const int q_n = q_noisy;
+    if (mu) {
+#pragma unroll
+        for (int p = 0; p < 3; p++) {
+            const int i = lane + 32 * p;
+            if (i < AECM_BINS) {
+                const int ch32 = st->ch_adapt32[i];
+                const uint32_t far = far_spec[i];
+                const uint32_t dfa = sc->dfa_noisy[i];
+                const int z_ch = norm_u32((uint32_t)ch32);
+                const int z_far = norm_u32(far);
+                uint32_t prod;
+                int sh_chfar;
+                if (z_ch + z_far > 31) {  // :836-850
+                    prod = (uint32_t)ch32 * far;
+                    sh_chfar = 0;
+                } else {
+                    sh_chfar = 32 - z_ch - z_far;
+                    prod = (uint32_t)(sh_chfar >= 32 ? 0 : ch32 >> sh_chfar) * far;
+                }
+                int z_num = norm_u32(prod);
+                const int z_dfa = dfa ? norm_u32(dfa) : 32;
+                const int t16 = z_dfa - 2 + q_n - kResCh32 - zx + sh_chfar;
+                int xq, dq;
+                if (z_num > t16 + 1) {  // :860-867
+                    xq = t16;
+                    dq = z_dfa - 2;
+                } else {
+                    xq = z_num - 2;
+                    dq = kResCh32 + zx - q_n - sh_chfar + xq;
+                }
+                prod = shift_u32(prod, xq);
+                const uint32_t dfa_al = shift_u32(dfa, dq);
+                const int err = (int)dfa_al - (int)prod;
+                z_num = norm_w32(err);
+                if (err && (far > (uint32_t)(kChannelVad << zx))) {  // :873
+                    int upd, sh_num;
+                    if (z_num + z_far > 31) {  // :886-902
+                        upd = err > 0 ? (int)((uint32_t)err * far) : -(int)((uint32_t)(-err) * far);
+                        sh_num = 0;
+                    } else {
+                        sh_num = 32 - (z_num + z_far);
+                        upd = err > 0 ? (err >> sh_num) * (int)far : -((-err >> sh_num) * (int)far);
+                    }
+                    upd = upd / (i + 1);  // :904
+                    const int sh2 = sh_num + sh_chfar - xq - mu - ((30 - z_far) << 1);
+                    if (norm_w32(upd) < sh2) upd = 0x7fffffff;  // :908-912
+                    else upd = shift_s32(upd, sh2);
+                    int nch = add_sat32(ch32, upd);
+                    if (nch < 0) nch = 0;
+                    st->ch_adapt32[i] = nch;
+                    st->ch_adapt16[i] = (int16_t)(nch >> 16);
+                }
+            }
+        }
+        __syncwarp();
+    }
+    bool do_store = false;
+    if ((S.startup_state == 0) & (S.current_vad != 0)) {  // :926-929
+        do_store = true;
+    } else {
+        if (far_log < S.far_e_mse) S.mse_channel_count = 0;
+        else S.mse_channel_count = s16(S.mse_channel_count + 1);
+        if (S.mse_channel_count >= kMinMseCount + 10) {  // :937-983
+            __syncwarp();
+            int ds = 0, da = 0;
+            if (lane < kMinMseCount) {
+                const int k = (lh + lane) & (AECM_LOG_RING - 1);
+                const int nl = st->near_log[k];
+                ds = abs((int)st->echo_stored_log[k] - nl);
+                da = abs((int)st->echo_adapt_log[k] - nl);
+            }
+            const int mse_stored = __reduce_add_sync(kFull, ds);
+            const int mse_adapt = __reduce_add_sync(kFull, da);
+            if (((mse_stored << kMseResolution) < (kMinMseDiff * mse_adapt)) &
+                ((S.mse_stored_old << kMseResolution) < (kMinMseDiff * S.mse_adapt_old))) {
+                // ResetAdaptiveChannel, aecm_core.cc:308-323
+#pragma unroll
+                for (int p = 0; p < 3; p++) {
+                    const int i = lane + 32 * p;
+                    if (i < AECM_BINS) {
+                        const int v = st->ch_stored[i];
+                        st->ch_adapt16[i] = (int16_t)v;
+                        st->ch_adapt32[i] = (int)((uint32_t)v << 16);
+                    }
+                }
+            } else if (((kMinMseDiff * mse_stored) > (mse_adapt << kMseResolution)) & (mse_adapt < S.mse_threshold) &
+                       (S.mse_adapt_old < S.mse_threshold)) {
+                do_store = true;
+                if (S.mse_threshold == 0x7fffffff) {
+                    S.mse_threshold = mse_adapt + S.mse_adapt_old;
+                } else {
+                    const int scaled = S.mse_threshold * 5 / 8;
+                    S.mse_threshold += ((mse_adapt - scaled) * 205) >> 8;
+                }
+            }
+            S.mse_channel_count = 0;
+            S.mse_stored_old = mse_stored;
+            S.mse_adapt_old = mse_adapt;
+        }
+    }
+    if (do_store) {  // StoreAdaptiveChannel, aecm_core.cc:286-306
+#pragma unroll
+        for (int p = 0; p < 3; p++) {
+            const int i = lane + 32 * p;
+            if (i < AECM_BINS) {
+                const int v = st->ch_adapt16[i];
+                st->ch_stored[i] = (int16_t)v;
+                sc->echo_est[i] = v * (int)far_spec[i];
+            }
+        }
+    }
+    __syncwarp();
+
+    // ---- CalcSuppressionGain (aecm_core.cc:1000-1052) ----
+    int sup_gain;
+    {
+        int g = kSupGainDefault;
+        if (!S.current_vad) {
+            g = 0;
+        } else {
+            const int t16 = s16((int)st->near_log[lh] - (int)st->echo_stored_log[lh]);
+            const int de = t16 >= 0 ? t16 : s16(-t16);
+            if (de < kEnergyDevTol) {
+                if (de < kSupGainEpcDt) {
+                    const int t32 = S.sup_diff_ab * de + (kSupGainEpcDt >> 1);
+                    g = s16(S.sup_a - s16(t32 / kSupGainEpcDt));
+                } else {
+                    const int t32 = S.sup_diff_bd * (kEnergyDevTol - de) + ((kEnergyDevTol - kSupGainEpcDt) >> 1);
+                    g = s16(S.sup_d + s16(t32 / (kEnergyDevTol - kSupGainEpcDt)));
+                }
+            } else {
+                g = S.sup_d;
+            }
+        }
+        const int t = g > S.sup_gain_old ? g : S.sup_gain_old;
+        S.sup_gain_old = g;
+        S.sup_gain = s16(S.sup_gain + s16((t - S.sup_gain) >> 4));
+        sup_gain = S.sup_gain;
+    }
+
+    // ---- Wiener gain per bin (aecm_core_c.cc:517-615) ----
+    int hnl[3];
+    int num_pos = 0;
+    const int dq_clean = s16(q_clean - q_clean_old);
+    const int z16_sup = norm_w16(sup_gain) + 1;
+#pragma unroll
+    for (int p = 0; p < 3; p++) {
+        const int i = lane + 32 * p;
+        hnl[p] = 0;
+        if (i < AECM_BINS) {
+            int ef = st->echo_filt[i];
+            const int diff = sc->echo_est[i] - ef;
+            ef += (int)(((long long)diff * 50) >> 8);  // :523-525
+            st->echo_filt[i] = ef;
+            const int z32 = norm_w32(ef) + 1;
+            uint32_t gained;
+            int res_diff;
+            if (z32 + z16_sup > 16) {  // :529-550
+                gained = (uint32_t)ef * (uint32_t)(uint16_t)sup_gain;
+                res_diff = 14 - kResCh16 - kResSupGain + (q_clean - zx);
+            } else {
+                const int t = 17 - z32 - z16_sup;
+                res_diff = 14 + t - kResCh16 - kResSupGain + (q_clean - zx);
+                if (z32 > t) gained = (uint32_t)ef * (uint32_t)(uint16_t)(sup_gain >> t);
+                else gained = (uint32_t)((ef >> t) * sup_gain);
+            }
+            const int nf = st->near_filt[i];
+            const int dfc = dfa_clean[i];
+            int z16 = norm_w16(nf);
+            int n1, n2, q_diff;
+            if (z16 < dq_clean && nf) {  // :556-566
+                n1 = s16(nf << z16);
+                q_diff = z16 - dq_clean;
+                n2 = s16(dfc >> -q_diff);
+            } else {
+                n1 = dq_clean < 0 ? nf >> -dq_clean : s16(nf << dq_clean);
+                q_diff = 0;
+                n2 = s16(dfc);
+            }
+            n2 = s16(s16((n2 - n1) >> 4) + n1);  // :567-570
+            z16 = norm_w16(n2);
+            int nfn;
+            if (n2 & (int)(-q_diff > z16)) nfn = 32767;  // :572 (bitwise and of the value with the flag)
+            else nfn = q_diff < 0 ? s16(n2 << -q_diff) : n2 >> q_diff;
+            st->near_filt[i] = (int16_t)nfn;
+            int h;
+            if (gained == 0) {  // :582-611
+                h = kOneQ14;
+            } else if (nfn == 0) {
+                h = 0;
+            } else {
+                gained += (uint32_t)(nfn >> 1);
+                const uint32_t ratio = gained / (uint32_t)(uint16_t)nfn;
+                const int t32 = (int)shift_u32(ratio, res_diff);
+                if (t32 > kOneQ14) h = 0;
+                else if (t32 < 0) h = kOneQ14;
+                else h = max(s16(kOneQ14 - s16(t32)), 0);
+            }
+            hnl[p] = h;
+            num_pos += (h != 0);
+        }
+    }
+    num_pos = __reduce_add_sync(kFull, num_pos);
+    if (S.mult == 2) {  // wideband only, :618-648
+        int part = 0;
+#pragma unroll
+        for (int p = 0; p < 3; p++) hnl[p] = (hnl[p] * hnl[p]) >> 14;
+        if (lane >= 4 && lane <= 24) part = hnl[0];
+        const int avg = __reduce_add_sync(kFull, part) / 21;
+#pragma unroll
+        for (int p = 0; p < 3; p++) {
+            const int i = lane + 32 * p;
+            if (i >= 24 && hnl[p] > avg) hnl[p] = avg;
+        }
+    }
+    // ---- NLP and gain application (aecm_core_c.cc:651-686; nlpFlag is 1 forever, aecm_core.cc:399) ----
+    int ere[3], eim[3];
+    const int nlp_gain = num_pos < 3 ? 0 : kOneQ14;
+#pragma unroll
+    for (int p = 0; p < 3; p++) {
+        const int i = lane + 32 * p;
+        ere[p] = eim[p] = 0;
+        if (i < AECM_BINS) {
+            int h = hnl[p];
+            if (h > kOneQ14) h = kOneQ14;
+            else if (h < kNlpLow) h = 0;
+            if (!(h == kOneQ14 && nlp_gain == kOneQ14)) h = (h * nlp_gain) >> 14;
+            hnl[p] = h;
+            const uint32_t d = sc->dfw[i];
+            ere[p] = s16((lo16(d) * h + 8192) >> 14);
+            eim[p] = s16((hi16(d) * h + 8192) >> 14);
+        }
+    }
+
+    // ---- ComfortNoise (aecm_core_c.cc:52-164) ----
+    if (S.cng_mode == 1) {
+        const int sh = 15 - q_clean;
+        int track;
+        if (S.noise_est_ctr < 100) { S.noise_est_ctr++; track = 6; } else { track = 9; }
+        const uint32_t seed = S.seed;
+#pragma unroll
+        for (int p = 0; p < 3; p++) {
+            const int i = lane + 32 * p;
+            if (i < AECM_BINS) {
+                int ne = st->noise_est[i];
+                int lo_c = st->noise_low_ctr[i], hi_c = st->noise_high_ctr[i];
+                const int lvl = (int)((uint32_t)dfa_clean[i] << sh);
+                if (lvl < ne) {  // :86-102
+                    lo_c = 0;
+                    if (ne < (1 << track)) {
+                        hi_c++;
+                        if (hi_c >= 5) { ne--; hi_c = 0; }
+                    } else {
+                        ne -= (ne - lvl) >> track;
+                    }
+                } else {  // :103-126
+                    hi_c = 0;
+                    if ((ne >> 19) > 0) { ne >>= 11; ne *= 2049; }
+                    else if ((ne >> 11) > 0) { ne *= 2049; ne >>= 11; }
+                    else {
+                        lo_c++;
+                        if (lo_c >= 5) { ne += (ne >> 9) + 1; lo_c = 0; }
+                    }
+                }
+                int t32 = ne >> sh;  // :130-139
+                if (t32 > 32767) { t32 = 32767; ne = t32 << sh; }
+                st->noise_est[i] = ne;
+                st->noise_low_ctr[i] = (uint8_t)lo_c;
+                st->noise_high_ctr[i] = (uint8_t)hi_c;
+                const int noise = s16((s16(kOneQ14 - hnl[p]) * t32) >> 14);
+                if (i > 0) {  // :146-163: bin 0 gets no noise, bin 64 only a real part
+                    const uint32_t r = (c.tab->lcg_mul[i - 1] * seed + c.tab->lcg_add[i - 1]) & 0x7fffffffu;
+                    const int rnd = (int)(r >> 16);
+                    const int idx = (359 * rnd) >> 15;
+                    const uint32_t cs = c.tab->cossin[idx];
+                    const int ur = s16((noise * lo16(cs)) >> 13);
+                    const int ui = i < 64 ? s16((-noise * hi16(cs)) >> 13) : 0;
+                    ere[p] = sat16(ere[p] + ur);
+                    eim[p] = sat16(eim[p] + ui);
+                }
+            }
+        }
+        S.seed = (c.tab->lcg_mul[63] * seed + c.tab->lcg_add[63]) & 0x7fffffffu;  // 64 draws per block, :143
+    }
+
+    // ---- InverseFFTAndWindow (aecm_core_c.cc:193-246, real_fft.c:74-102) ----
+    int peak = 0;
+#pragma unroll
+    for (int p = 0; p < 3; p++) {
+        const int i = lane + 32 * p;
+        if (i < AECM_BINS) {
+            const int nim = s16(-eim[p]);  // aecm_core_c.cc:206-214
+            sc->fft[brev7(i)] = pack16(ere[p], nim);
+            peak = max(peak, max(abs(ere[p]), abs(nim)));
+            if (i > 0 && i < 64) sc->fft[brev7(128 - i)] = pack16(ere[p], s16(-nim));  // real_fft.c:87-91
+        }
+    }
+    peak = min(__reduce_max_sync(kFull, peak), 32767);
+    __syncwarp();
+    const int scale = fft128_inverse(sc->fft, c.tab->twiddle, lane, peak);
+    const int cshift = scale - q_clean;
+#pragma unroll
+    for (int h = 0; h < 2; h++) {
+        const int i = lane + 32 * h;
+        const int w0 = c.tab->hann[i], w1 = c.tab->hann[64 - i];
+        int t32 = s16((lo16(sc->fft[i]) * w0 + 8192) >> 14);  // :219-221
+        t32 = shift_s32(t32, cshift);
+        sc->out_blk[i] = (int16_t)sat16(t32 + (int)st->out_ola[i]);  // :224-227
+        t32 = (lo16(sc->fft[64 + i]) * w1) >> 14;  // :229-230 (no rounding here)
+        t32 = shift_s32(t32, cshift);
+        st->out_ola[i] = (int16_t)sat16(t32);
+        // slide the analysis buffers, :239-245
+        st->x_old[i] = st->frm_far[wrap_add(in_rd, i, AECM_FRM_RING)];
+        st->d_noisy_old[i] = st->frm_near[wrap_add(in_rd, i, AECM_FRM_RING)];
+        if (use_clean) st->d_clean_old[i] = st->frm_clean[wrap_add(clean_rd, i, AECM_FRM_RING)];
+    }
+    __syncwarp();
+}
+
+// ------------------------------------------------------------------------------------------------
+// FIFO helpers: a FIFO is (storage, capacity, read index, fill count) -- ring_buffer.c:53-231
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ int fifo_move(int &rd, int &cnt, int cap, int k) {  // ring_buffer.c:177-212
+    const int room = cap - cnt;
+    if (k > cnt) k = cnt;
+    if (k < -room) k = -room;
+    int r = rd + k;
+    if (r >= cap) r -= cap;
+    if (r < 0) r += cap;
+    rd = r;
+    cnt -= k;
+    return k;
+}
+
+// ------------------------------------------------------------------------------------------------
+// L2: one 80-sample frame (aecm_core.cc:501-572).  The far frame comes from the HBM jitter FIFO (far_idx >= 0:
+// index of its first sample) or from the replay buffer farend_old[slot]; near/clean come from the input planes.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void process_frame(const Ctx &c, int far_idx, int slot, const int16_t *near80,
+                                              const int16_t *clean80, int16_t *out80) {
+    AecmInstanceState *st = c.st;
+    AecmScalars &S = st->s;
+    const int lane = c.lane;
+    {   // WebRtc_WriteBuffer x2/x3, :520-524 (a full FIFO drops the excess, ring_buffer.c:150-152)
+        const int n = min(AECM_FRAME_LEN, AECM_FRM_RING - S.frm_in_cnt);
+        const int wr = wrap_add(S.frm_in_rd, S.frm_in_cnt, AECM_FRM_RING);
+        for (int k = lane; k < n; k += 32) {
+            const int16_t f = far_idx >= 0 ? c.far_ring[wrap_add(far_idx, k, AECM_FAR_RING)] : st->farend_old[slot][k];
+            if (far_idx >= 0) st->farend_old[slot][k] = f;  // echo_control_mobile.cc:374
+            const int w = wrap_add(wr, k, AECM_FRM_RING);
+            st->frm_far[w] = f;
+            st->frm_near[w] = near80[k];
+        }
+        S.frm_in_cnt += n;
+        if (clean80) {
+            const int nc = min(AECM_FRAME_LEN, AECM_FRM_RING - S.frm_clean_cnt);
+            const int wc = wrap_add(S.frm_clean_rd, S.frm_clean_cnt, AECM_FRM_RING);
+            for (int k = lane; k < nc; k += 32) st->frm_clean[wrap_add(wc, k, AECM_FRM_RING)] = clean80[k];
+            S.frm_clean_cnt += nc;
+        }
+    }
+    __syncwarp();
+    while (S.frm_in_cnt >= AECM_PART_LEN) {  // :527-555
+        const int in_rd = S.frm_in_rd;
+        const int clean_rd = S.frm_clean_rd;
+        process_block(c, in_rd, clean_rd, clean80 != nullptr);
+        fifo_move(S.frm_in_rd, S.frm_in_cnt, AECM_FRM_RING, AECM_PART_LEN);
+        if (clean80) fifo_move(S.frm_clean_rd, S.frm_clean_cnt, AECM_FRM_RING, AECM_PART_LEN);
+        const int n = min(AECM_PART_LEN, AECM_FRM_RING - S.frm_out_cnt);
+        const int wr = wrap_add(S.frm_out_rd, S.frm_out_cnt, AECM_FRM_RING);
+        for (int k = lane; k < n; k += 32) st->frm_out[wrap_add(wr, k, AECM_FRM_RING)] = c.sc->out_blk[k];
+        S.frm_out_cnt += n;
+        __syncwarp();
+    }
+    if (S.frm_out_cnt < AECM_FRAME_LEN)  // :559-562: rewind, re-emitting already delivered samples
+        fifo_move(S.frm_out_rd, S.frm_out_cnt, AECM_FRM_RING, S.frm_out_cnt - AECM_FRAME_LEN);
+    {
+        const int n = min(AECM_FRAME_LEN, S.frm_out_cnt);
+        const int rd = S.frm_out_rd;
+        for (int k = lane; k < n; k += 32) out80[k] = st->frm_out[wrap_add(rd, k, AECM_FRM_RING)];
+        fifo_move(S.frm_out_rd, S.frm_out_cnt, AECM_FRM_RING, n);
+    }
+    __syncwarp();
+}
+
+// ------------------------------------------------------------------------------------------------
+// L3: WebRtcAecm_BufferFarend (echo_control_mobile.cc:215-234) and WebRtcAecm_Process (:236-408)
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ int api_buffer_farend(const Ctx &c, const int16_t *far, int n) {
+    AecmScalars &S = c.st->s;
+    if (S.init_flag != AECM_INIT_MAGIC) return AECM_UNINITIALIZED_ERROR;
+    if (!S.ec_startup) {  // WebRtcAecm_DelayComp, :575-594
+        const int n_far = S.far_cnt;
+        const int n_snd = S.ms_in_snd_card_buf * 8 * S.mult;
+        if (n_snd - n_far > 4 * AECM_PART_LEN - AECM_FRAME_LEN * S.mult) {
+            int add = max((n_snd >> 1) - n_far, AECM_FRAME_LEN);
+            add = min(add, 10 * AECM_FRAME_LEN);
+            fifo_move(S.far_rd, S.far_cnt, AECM_FAR_RING, -add);
+            S.delay_change = 1;
+        }
+    }
+    const int w = min(n, AECM_FAR_RING - S.far_cnt);
+    int wr = S.far_rd + S.far_cnt;
+    if (wr >= AECM_FAR_RING) wr -= AECM_FAR_RING;
+    for (int k = c.lane; k < w; k += 32) c.far_ring[wrap_add(wr, k, AECM_FAR_RING)] = far[k];
+    S.far_cnt += w;
+    __syncwarp();
+    return 0;
+}
+
+__device__ __forceinline__ void est_buf_delay(AecmScalars &S) {  // echo_control_mobile.cc:534-573
+    const int n_far = s16(S.far_cnt);
+    const int n_snd = s16(S.ms_in_snd_card_buf * 8 * S.mult);
+    int delay_new = s16(n_snd - n_far);
+    if (delay_new < AECM_FRAME_LEN) {
+        fifo_move(S.far_rd, S.far_cnt, AECM_FAR_RING, AECM_FRAME_LEN);
+        delay_new = s16(delay_new + AECM_FRAME_LEN);
+    }
+    S.filt_delay = s16(max(0, (8 * S.filt_delay + 2 * delay_new) / 10));
+    const int diff = s16(S.filt_delay - S.wrapper_known_delay);
+    if (diff > 224) {
+        if (S.last_delay_diff < 96) S.time_for_delay_change = 0; else S.time_for_delay_change++;
+    } else if (diff < 96 && S.wrapper_known_delay > 0) {
+        if (S.last_delay_diff > 224) S.time_for_delay_change = 0; else S.time_for_delay_change++;
+    } else {
+        S.time_for_delay_change = 0;
+    }
+    S.last_delay_diff = diff;
+    if (S.time_for_delay_change > 25) S.wrapper_known_delay = max(S.filt_delay - 160, 0);  // never forwarded (:390-391)
+}
+
+__device__ __forceinline__ int api_process(const Ctx &c, const int16_t *near_noisy, const int16_t *near_clean,
+                                           int16_t *out, int n, int ms) {
+    AecmScalars &S = c.st->s;
+    const int lane = c.lane;
+    int ret = 0;
+    if (S.init_flag != AECM_INIT_MAGIC) return AECM_UNINITIALIZED_ERROR;
+    if (ms < 0) { ms = 0; ret = AECM_BAD_PARAMETER_WARNING; }          // :272-278
+    else if (ms > 500) { ms = 500; ret = AECM_BAD_PARAMETER_WARNING; }
+    ms += 10;
+    S.ms_in_snd_card_buf = ms;
+    const int n_frames = n / AECM_FRAME_LEN;
+    const int n_blocks10ms = n_frames / S.mult;
+
+    if (S.ec_startup) {  // :285-356
+        const int16_t *src = near_clean ? near_clean : near_noisy;
+        if (out != src)
+            for (int k = lane; k < n; k += 32) out[k] = src[k];
+        const int filled = s16(S.far_cnt) / AECM_FRAME_LEN;
+        if (S.check_buff_size) {
+            S.check_buf_size_ctr = s16(S.check_buf_size_ctr + 1);
+            if (S.counter == 0) { S.first_val = ms; S.sum = 0; }
+            const int dev = abs(S.first_val - ms);
+            const double tol = 0.2 * ms > 8 ? 0.2 * ms : 8;  // :312-313, a double comparison in the reference
+            if ((double)dev < tol) { S.sum = s16(S.sum + ms); S.counter = s16(S.counter + 1); }
+            else S.counter = 0;
+            if (S.counter * n_blocks10ms >= 6) {
+                S.buf_size_start = s16(min((3 * S.sum * S.mult) / (S.counter * 40), 50));
+                S.check_buff_size = 0;
+            }
+            if (S.check_buf_size_ctr * n_blocks10ms > 50) {
+                S.buf_size_start = s16(min((3 * ms * S.mult) / 40, 50));
+                S.check_buff_size = 0;
+            }
+        }
+        if (!S.check_buff_size) {
+            if (filled == S.buf_size_start) {
+                S.ec_startup = 0;
+            } else if (filled > S.buf_size_start) {
+                fifo_move(S.far_rd, S.far_cnt, AECM_FAR_RING, S.far_cnt - S.buf_size_start * AECM_FRAME_LEN);
+                S.ec_startup = 0;
+            }
+        }
+    } else {  // :358-397
+        for (int i = 0; i < n_frames; i++) {
+            const int filled = s16(S.far_cnt) / AECM_FRAME_LEN;
+            int far_idx = -1;
+            if (filled > 0) {  // WebRtc_ReadBuffer of 80 samples
+                far_idx = S.far_rd;
+                fifo_move(S.far_rd, S.far_cnt, AECM_FAR_RING, AECM_FRAME_LEN);
+            }
+            if ((i == 0 && S.fs == 8000) || (i == 1 && S.fs == 16000)) est_buf_delay(S);
+            process_frame(c, far_idx, i, near_noisy + AECM_FRAME_LEN * i,
+                          near_clean ? near_clean + AECM_FRAME_LEN * i : nullptr, out + AECM_FRAME_LEN * i);
+        }
+    }
+    return ret;
+}
+
+// ------------------------------------------------------------------------------------------------
+// kernels
+// ------------------------------------------------------------------------------------------------
+struct __align__(16) CtaShared {
+    CtaTables tab;
+    uint32_t pad_[2];
+};
+
+__device__ __forceinline__ void load_tables(CtaTables *t) {
+    for (int k = threadIdx.x; k < 64; k += blockDim.x) {
+        t->twiddle[k] = kAecmTwiddle128[k];
+        t->lcg_mul[k] = kLcgJump.mul[k];
+        t->lcg_add[k] = kLcgJump.add[k];
+    }
+    for (int k = threadIdx.x; k < 360; k += blockDim.x) t->cossin[k] = kAecmCosSinQ13[k];
+    for (int k = threadIdx.x; k < 65; k += blockDim.x) t->hann[k] = kAecmSqrtHanningQ14[k];
+}
+
+// shared memory: [CtaShared][kWarpsPerCta x (AecmInstanceState, WarpScratch)]
+__global__ void __launch_bounds__(kWarpsPerCta * 32) aecm_call_kernel(AecmBatchPlanes planes, AecmCallArgs a) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    CtaShared *cs = reinterpret_cast<CtaShared *>(smem_raw);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    unsigned char *wbase = smem_raw + sizeof(CtaShared) + (size_t)warp * (sizeof(AecmInstanceState) + sizeof(WarpScratch));
+    AecmInstanceState *st = reinterpret_cast<AecmInstanceState *>(wbase);
+    WarpScratch *sc = reinterpret_cast<WarpScratch *>(wbase + sizeof(AecmInstanceState));
+
+    load_tables(&cs->tab);
+    const int row = blockIdx.x * kWarpsPerCta + warp;
+    const bool active = row < a.count;
+    const int inst = a.first + row;
+    const bool use_clean = a.near_clean != nullptr;
+    const int n_vec = (use_clean ? AECM_STATE_BYTES : AECM_STATE_BYTES_NOCLEAN) / 16;
+    uint4 *g_state = reinterpret_cast<uint4 *>(planes.state + (active ? inst : 0));
+    if (active) {
+        uint4 *s_state = reinterpret_cast<uint4 *>(st);
+        for (int k = lane; k < n_vec; k += 32) s_state[k] = g_state[k];
+    }
+    __syncthreads();
+    if (!active) return;
+
+    Ctx c;
+    c.st = st;
+    c.sc = sc;
+    c.tab = &cs->tab;
+    c.far_hist = planes.far_hist + (size_t)inst * AECM_MAX_DELAY * AECM_HIST_ROW;
+    c.far_ring = planes.far_ring + (size_t)inst * AECM_FAR_RING;
+    c.lane = lane;
+
+    const int64_t off = (int64_t)row * a.row_stride;
+    const int ms = a.ms ? (int)a.ms[row] : a.ms_uniform;
+    int status = 0;
+    for (int call = 0; call < a.n_calls; call++) {
+        const int64_t o = off + (int64_t)call * a.samples_per_call;
+        if (a.far && (!a.far_mask || a.far_mask[(size_t)call * a.count + row])) {
+            const int r = api_buffer_farend(c, a.far + o, a.samples_per_call);
+            if (status == 0) status = r;
+        }
+        if (a.near_noisy) {
+            const int r = api_process(c, a.near_noisy + o, use_clean ? a.near_clean + o : nullptr, a.out + o,
+                                      a.samples_per_call, ms);
+            if (status == 0) status = r;
+        }
+    }
+    __syncwarp();
+    {
+        const uint4 *s_state = reinterpret_cast<const uint4 *>(st);
+        for (int k = lane; k < n_vec; k += 32) g_state[k] = s_state[k];
+    }
+    if (a.status && lane == 0) a.status[row] = status;
+}
+
+// WebRtcAecm_Init (echo_control_mobile.cc:142-191) + WebRtcAecm_InitCore (aecm_core.cc:358-473) +
+// delay-estimator init (delay_estimator.cc:330-334, 483-504; delay_estimator_wrapper.cc:208-225, 338-355).
+// One warp per instance, working directly on the HBM record (far_hist / far_ring are zeroed by memset).
+__device__ void init_echo_path_core(AecmInstanceState *g, const int16_t *path, int lane) {  // aecm_core.cc:249-265
+    for (int i = lane; i < AECM_BINS; i += 32) {
+        const int v = path[i];
+        g->ch_stored[i] = (int16_t)v;
+        g->ch_adapt16[i] = (int16_t)v;
+        g->ch_adapt32[i] = (int)((uint32_t)v << 16);
+    }
+    if (lane == 0) {
+        g->s.mse_adapt_old = 1000;
+        g->s.mse_stored_old = 1000;
+        g->s.mse_threshold = 0x7fffffff;
+        g->s.mse_channel_count = 0;
+    }
+}
+
+__device__ void apply_config(AecmScalars &S, int cng_mode, int echo_mode) {  // echo_control_mobile.cc:431-476
+    const int rs = echo_mode < 3 ? 3 - echo_mode : 0, ls = echo_mode == 4 ? 1 : 0;
+    const int def = (kSupGainDefault >> rs) << ls, pa = (kSupGainA >> rs) << ls, pb = (kSupGainB >> rs) << ls,
+              pd = (kSupGainD >> rs) << ls;
+    S.cng_mode = cng_mode;
+    S.echo_mode = echo_mode;
+    S.sup_gain = def;
+    S.sup_gain_old = def;
+    S.sup_a = pa;
+    S.sup_d = pd;
+    S.sup_diff_ab = pa - pb;
+    S.sup_diff_bd = pb - pd;
+}
+
+__global__ void aecm_init_kernel(AecmBatchPlanes planes, int first, int count, int fs) {
+    const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (row >= count) return;
+    AecmInstanceState *g = planes.state + first + row;
+    uint32_t *w = reinterpret_cast<uint32_t *>(g);
+    for (int k = lane; k < AECM_STATE_BYTES / 4; k += 32) w[k] = 0;
+    __syncwarp();
+    for (int k = lane; k < AECM_MAX_DELAY; k += 32) g->mean_bit_counts[k] = 20 << 9;  // delay_estimator.cc:490-493
+    // pink-ish initial noise floor, aecm_core.cc:428-435: noiseEst[i] = (65 - i)^2 << 8 for i < 31, then flat
+    for (int i = lane; i < AECM_BINS; i += 32) {
+        const int k = i < 31 ? i : 31;
+        g->noise_est[i] = ((AECM_BINS - k) * (AECM_BINS - k)) << 8;
+    }
+    init_echo_path_core(g, fs == 8000 ? kAecmChannelInit8k : kAecmChannelInit16k, lane);
+    __syncwarp();
+    if (lane == 0) {
+        AecmScalars &S = g->s;
+        S.mult = fs / 8000;
+        S.seed = 666;
+        S.first_vad = 1;
+        S.far_e_min = 32767;
+        S.far_e_max = -32768;
+        S.far_e_vad = kFarEnergyMin;
+        S.far_hist_pos = AECM_MAX_DELAY;
+        S.minimum_probability = 32 << 9;
+        S.last_delay_probability = 32 << 9;
+        S.last_delay = -2;
+        S.fs = fs;
+        S.init_flag = AECM_INIT_MAGIC;
+        S.delay_change = 1;
+        S.check_buff_size = 1;
+        S.ec_startup = 1;
+        apply_config(S, 1, 3);  // default config, echo_control_mobile.cc:183-188
+    }
+}
+
+__global__ void aecm_set_config_kernel(AecmBatchPlanes planes, int first, int count, int cng_mode, int echo_mode,
+                                       int32_t *status) {
+    const int row = blockIdx.x * blockDim.x + threadIdx.x;
+    if (row >= count) return;
+    AecmScalars &S = planes.state[first + row].s;
+    int r = 0;
+    if (S.init_flag != AECM_INIT_MAGIC) {
+        r = AECM_UNINITIALIZED_ERROR;
+    } else if (cng_mode != 0 && cng_mode != 1) {
+        r = AECM_BAD_PARAMETER_ERROR;
+    } else if (echo_mode < 0 || echo_mode > 4) {
+        S.cng_mode = cng_mode;  // the reference assigns cngMode before validating echoMode (:424-428)
+        r = AECM_BAD_PARAMETER_ERROR;
+    } else {
+        apply_config(S, cng_mode, echo_mode);
+    }
+    if (status) status[row] = r;
+}
+
+__global__ void aecm_init_echo_path_kernel(AecmBatchPlanes planes, int first, int count, const int16_t *path,
+                                           int path_stride, int32_t *status) {
+    const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (row >= count) return;
+    AecmInstanceState *g = planes.state + first + row;
+    int r = 0;
+    if (g->s.init_flag != AECM_INIT_MAGIC) r = AECM_UNINITIALIZED_ERROR;  // echo_control_mobile.cc:496-498
+    else init_echo_path_core(g, path + (size_t)row * path_stride, lane);
+    if (status && lane == 0) status[row] = r;
+}
+
+int g_launches = 0;
+
+}  // namespace
+
+extern "C" {
+
+int aecm_cuda_kernel_launch_count(void) { return g_launches; }
+
+int aecm_cuda_launch_init(const AecmBatchPlanes *p, int first, int count, int samp_freq, void *stream) {
+    if (count <= 0) return 0;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    cudaError_t e = cudaMemsetAsync(p->far_hist + (size_t)first * AECM_MAX_DELAY * AECM_HIST_ROW, 0,
+                                    (size_t)count * AECM_MAX_DELAY * AECM_HIST_ROW * sizeof(uint16_t), s);
+    if (e != cudaSuccess) return (int)e;
+    e = cudaMemsetAsync(p->far_ring + (size_t)first * AECM_FAR_RING, 0, (size_t)count * AECM_FAR_RING * sizeof(int16_t), s);
+    if (e != cudaSuccess) return (int)e;
+    const int threads = 128, warps_per_block = threads / 32;
+    aecm_init_kernel<<<(count + warps_per_block - 1) / warps_per_block, threads, 0, s>>>(*p, first, count, samp_freq);
+    g_launches++;
+    return (int)cudaGetLastError();
+}
+
+int aecm_cuda_launch_set_config(const AecmBatchPlanes *p, int first, int count, int cng_mode, int echo_mode,
+                                int32_t *status, void *stream) {
+    if (count <= 0) return 0;
+    aecm_set_config_kernel<<<(count + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(*p, first, count, cng_mode,
+                                                                                                echo_mode, status);
+    g_launches++;
+    return (int)cudaGetLastError();
+}
+
+int aecm_cuda_launch_init_echo_path(const AecmBatchPlanes *p, int first, int count, const int16_t *d_path,
+                                    int path_stride, int32_t *status, void *stream) {
+    if (count <= 0) return 0;
+    const int threads = 128, warps_per_block = threads / 32;
+    aecm_init_echo_path_kernel<<<(count + warps_per_block - 1) / warps_per_block, threads, 0,
+                                 static_cast<cudaStream_t>(stream)>>>(*p, first, count, d_path, path_stride, status);
+    g_launches++;
+    return (int)cudaGetLastError();
+}
+
+int aecm_cuda_launch_call(const AecmBatchPlanes *p, const AecmCallArgs *a, void *stream) {
+    if (a->count <= 0 || a->n_calls <= 0) return 0;
+    static bool attr_set = false;
+    const size_t smem = sizeof(CtaShared) + (size_t)kWarpsPerCta * (sizeof(AecmInstanceState) + sizeof(WarpScratch));
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(aecm_call_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return (int)e;
+        attr_set = true;
+    }
+    const int blocks = (a->count + kWarpsPerCta - 1) / kWarpsPerCta;
+    aecm_call_kernel<<<blocks, kWarpsPerCta * 32, smem, static_cast<cudaStream_t>(stream)>>>(*p, *a);
+    g_launches++;
+    return (int)cudaGetLastError();
+}
+
+}  // extern "C"
