@@ -1,0 +1,361 @@
+#!/usr/bin/env python3
+"""bench.py -- AECM blocks/s on B200 (our arm) and on the host cores (reference arm).
+
+A *step* is one lockstep 10 ms API call -- WebRtcAecm_BufferFarend + WebRtcAecm_Process for every instance of
+the batch (BASELINE.json configs[1]: batch=4096 AecmCore instances per GPU, 16 kHz, synthetic echo) -- i.e. one
+launch of the fused kernel, 2 or 3 64-sample blocks per instance (2.5 on average).  ``--calls-per-step K``
+fuses K consecutive calls into one launch (offline/batched mode; reported in ``config``).
+
+  value      device-resident inputs, CUDA events per step on the launch stream, L2 flushed between steps
+  e2e        AecmB200_ProcessStream with pinned HOST planes: H2D of far+near and D2H of out inside the timing
+  roofline   algorithmic bytes (5940 B/block) / mean kernel time vs the measured HBM peak
+  cpu_baseline  the unmodified reference (oracle/_ref) on the host cores, bounded sample, rank 0 at N=1 only
+
+``--impl reference`` times the reference's own C implementation on all host cores for the same workload.
+Under torchrun every rank owns one GPU and an independent shard of instances (no collective on the data path);
+time is the max over ranks, value is the whole-job aggregate.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+ALGO_BYTES_PER_BLOCK = 5940  # ~3231 B read + ~2709 B written per block per instance
+PREP_CALLS = 440             # > 1024 blocks: startupState == 2, far-end VAD and channel store logic in steady state
+SEED = 0xAEC2
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=4096, help="instances per GPU (BASELINE configs[1])")
+    ap.add_argument("--fs", type=int, default=16000)
+    ap.add_argument("--calls-per-step", type=int, default=1)
+    ap.add_argument("--no-flush", action="store_true", help="do not flush L2 between steps")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+def load_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks/throttle reasons sampled every 200 ms while the timed region runs."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.gpu = gpu_index
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "200", "-i", str(self.gpu)], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+        except OSError:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            out, _ = self.proc.communicate(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+            out, _ = self.proc.communicate()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in out.strip().splitlines():
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(names, f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ---------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+
+    from webrtc_aecm_b200 import AecmBatch, api
+    from webrtc_aecm_b200.synth import synth_streams_torch
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (the AECM engine has no CPU path)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    B, fs, cps = args.batch, args.fs, args.calls_per_step
+    spc = 160 if fs == 16000 else 80
+    K, W = args.steps, args.warmup
+    first_inst = rank * B  # weak scaling: every rank owns B instances of one global instance numbering
+
+    batch = AecmBatch(B, local)
+    stream = torch.cuda.current_stream(dev)
+    batch.adopt_cuda_stream(stream.cuda_stream)  # so torch.cuda.Event brackets exactly our launches
+    assert batch.init(fs) == 0
+    rc, st = batch.set_config(1, 3)
+    assert rc == 0 and not st.any()
+    d_status = torch.zeros(B, dtype=torch.int32, device=dev)
+
+    # ---- untimed preparation: run the streams into steady state, chunked so HBM use stays small ----
+    sample0 = 0
+    chunk_calls = 40
+    for c0 in range(0, PREP_CALLS, chunk_calls):
+        far, near = synth_streams_torch(B, chunk_calls * spc, fs, SEED, 40, "echo", first_inst, sample0, dev)
+        out = torch.empty_like(near)
+        rc = batch.process_stream_device(far, near, None, out, row_stride=chunk_calls * spc, samples_per_call=spc,
+                                         n_calls=chunk_calls, d_status=d_status)
+        assert rc == 0
+        sample0 += chunk_calls * spc
+    torch.cuda.synchronize(dev)
+    assert int(d_status.abs().max().item()) == 0
+    st0 = batch.read_state(0)
+    assert st0.s.startup_state == 2 and st0.s.ec_startup == 0
+
+    # ---- timed streams: (W + K) steps of fresh audio, resident in HBM ----
+    n_calls_total = (W + K) * cps
+    far, near = synth_streams_torch(B, n_calls_total * spc, fs, SEED, 40, "echo", first_inst, sample0, dev)
+    out = torch.empty_like(near)
+    row_stride = n_calls_total * spc
+    flush = None if args.no_flush else torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+
+    def step(k):
+        return batch.process_stream_device(far, near, None, out, row_stride=row_stride, samples_per_call=spc,
+                                           n_calls=cps, d_status=d_status, sample_offset=k * cps * spc)
+
+    for k in range(W):
+        if flush is not None:
+            flush.zero_()
+        assert step(k) == 0
+    torch.cuda.synchronize(dev)
+    blocks_before = batch.read_state(0).s.tot_count
+    launches_before = api.lib().AecmB200_KernelLaunchCount()
+    ev0 = [torch.cuda.Event(enable_timing=True) for _ in range(K)]
+    ev1 = [torch.cuda.Event(enable_timing=True) for _ in range(K)]
+    sampler = ClockSampler(local)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize(dev)
+    sampler.start()
+    wall0 = time.perf_counter()
+    for k in range(K):
+        if flush is not None:
+            flush.zero_()  # > L2 (126 MB): every step starts with a cold L2
+        ev0[k].record(stream)
+        rc = step(W + k)
+        ev1[k].record(stream)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize(dev)
+    wall1 = time.perf_counter()
+    clocks = sampler.stop()
+    assert rc == 0 and int(d_status.abs().max().item()) == 0
+    launches = api.lib().AecmB200_KernelLaunchCount() - launches_before
+    step_ms = np.array([a.elapsed_time(b) for a, b in zip(ev0, ev1)])
+    dev_ms = float(step_ms.sum())
+    blocks_per_inst = batch.read_state(0).s.tot_count - blocks_before
+    t = torch.tensor([dev_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    max_ms = float(t.item())
+    total_blocks = blocks_per_inst * B * world
+    value = total_blocks / (max_ms * 1e-3)
+
+    # ---- e2e: host planes through the public C ABI (H2D + kernel + D2H + sync per step) ----
+    e2e = None
+    if not args.no_e2e:
+        Ke = min(K, 50)
+        hfar = torch.empty((B, cps * spc), dtype=torch.int16).pin_memory()
+        hnear = torch.empty_like(hfar).pin_memory()
+        hout = torch.empty_like(hfar).pin_memory()
+        hstatus = np.zeros(B, dtype=np.int32)
+        # continue the same streams: regenerate fresh audio for the e2e steps
+        efar, enear = synth_streams_torch(B, (Ke + 3) * cps * spc, fs, SEED, 40, "echo", first_inst,
+                                          sample0 + n_calls_total * spc, dev)
+        efar_h = efar.cpu().pin_memory()
+        enear_h = enear.cpu().pin_memory()
+        L = api.lib()
+        import ctypes as C
+
+        def e2e_step(k):
+            a = api.StreamArgs(hfar.data_ptr(), hnear.data_ptr(), None, hout.data_ptr(), cps * spc, 0, B, spc, cps, None, 40,
+                               None, hstatus.ctypes.data)
+            # the step's inputs arrive in pinned host memory (copied here from the pre-generated host stream)
+            hfar.copy_(efar_h[:, k * cps * spc:(k + 1) * cps * spc])
+            hnear.copy_(enear_h[:, k * cps * spc:(k + 1) * cps * spc])
+            t0 = time.perf_counter()
+            r = L.AecmB200_ProcessStream(batch._h, C.byref(a))
+            t1 = time.perf_counter()
+            assert r == 0 and not hstatus.any()
+            return t1 - t0
+
+        for k in range(3):
+            e2e_step(k)
+        b0 = batch.read_state(0).s.tot_count
+        if world > 1:
+            dist.barrier()
+        secs = sum(e2e_step(3 + k) for k in range(Ke))
+        tt = torch.tensor([secs], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        eb = (batch.read_state(0).s.tot_count - b0) * B * world
+        e2e = {"value": eb / float(tt.item()), "unit": "blocks/s", "h2d_bytes_per_step": 2 * B * cps * spc * 2,
+               "d2h_bytes_per_step": B * cps * spc * 2 + B * 4, "steps": Ke,
+               "note": "AecmB200_ProcessStream on pinned host planes: H2D far+near, fused kernel, D2H out+status, stream sync"}
+
+    # ---- CPU baseline beside it (rank 0, N=1 only) ----
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cpu = cpu_reference_throughput(fs, spc, n_inst=1024, prep_calls=PREP_CALLS, timed_calls=160)
+
+    if rank == 0:
+        peak, peak_src = load_peaks()
+        blocks_per_launch = blocks_per_inst * B / K
+        kernel_s = dev_ms * 1e-3 / K  # one launch per step
+        achieved = blocks_per_launch * ALGO_BYTES_PER_BLOCK / kernel_s / 1e9
+        line = {
+            "metric": "AECM blocks/sec (64-sample, 16 kHz) across batch; bit-exact",
+            "value": value, "unit": "blocks/s", "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": max_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "int16/int32 Q-format", "data": "synthetic",
+            "config": {"workload": f"batch={B} AecmCore instances per GPU, {fs} Hz, synthetic echo, cng=1 echoMode=3, "
+                                   f"msInSndCardBuf=40, steady state (startupState=2)",
+                       "step": f"{cps} lockstep 10 ms call(s) (BufferFarend+Process) per launch",
+                       "batch_per_gpu": B, "calls_per_step": cps, "blocks_per_instance_per_step": blocks_per_inst / K,
+                       "l2": "inputs fresh every step; L2 flushed (256 MiB memset) between steps" if flush is not None
+                       else "inputs fresh every step; L2 not flushed",
+                       "realtime_channels": value / (250.0 if fs == 16000 else 125.0)},
+            "clocks": clocks, "gpu_launches": int(launches),
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": None, "peak_source": peak_src,
+                         "algorithmic_bytes_per_block": ALGO_BYTES_PER_BLOCK, "blocks_per_launch": blocks_per_launch,
+                         "kernel_ms": kernel_s * 1e3,
+                         "note": "integer-issue bound kernel; see DESIGN.md for the issue-slot roofline"},
+            "wall_ms_per_step": (wall1 - wall0) * 1e3 / K,
+        }
+        if e2e:
+            line["e2e"] = e2e
+        if cpu:
+            line["cpu_baseline"] = cpu
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def cpu_reference_throughput(fs, spc, n_inst, prep_calls, timed_calls, threads=None):
+    """Blocks/s of the reference's C path on the host cores for the same workload (bounded sample)."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import oracle_lib as ol
+    from webrtc_aecm_b200.synth import synth_streams
+
+    threads = threads or (os.cpu_count() or 1)
+    kind = "reference" if ol.ref_path() else "port"
+    pool = ol.CpuPool(n_inst, fs=fs, impl="ref" if kind == "reference" else "oracle", cng_mode=1, echo_mode=3,
+                      threads=threads)
+    total = prep_calls + timed_calls
+    # numpy generation is slow: make 64 distinct streams and tile them over the pool
+    base = min(n_inst, 64)
+    far, near = synth_streams(base, total * spc, fs, SEED, 40, "echo")
+    reps = (n_inst + base - 1) // base
+    far = np.ascontiguousarray(np.tile(far, (reps, 1))[:n_inst])
+    near = np.ascontiguousarray(np.tile(near, (reps, 1))[:n_inst])
+    pool.run(np.ascontiguousarray(far[:, :prep_calls * spc]), np.ascontiguousarray(near[:, :prep_calls * spc]),
+             samples_per_call=spc)
+    _, acc, secs = pool.run(np.ascontiguousarray(far[:, prep_calls * spc:]), np.ascontiguousarray(near[:, prep_calls * spc:]),
+                            samples_per_call=spc)
+    pool.close()
+    blocks = n_inst * timed_calls * spc / 64.0
+    return {"value": blocks / secs, "unit": "blocks/s", "cores": threads, "kind": kind,
+            "sample": f"{n_inst} instances x {timed_calls} steady-state 10 ms calls ({blocks:.0f} blocks) after "
+                      f"{prep_calls} warm-up calls, {threads} threads, instances statically sharded",
+            "seconds": secs, "return_codes_or": int(acc)}
+
+
+def run_reference(args):
+    """The reference arm: the reference's own C implementation on the host cores, same workload/metric."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    fs, cps = args.fs, args.calls_per_step
+    spc = 160 if fs == 16000 else 80
+    K, W = args.steps, args.warmup
+    B = args.batch
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import oracle_lib as ol
+    from webrtc_aecm_b200.synth import synth_streams
+
+    threads = os.cpu_count() or 1
+    kind = "reference" if ol.ref_path() else "port"
+    # bounded sample of the workload: a slice of the batch sized so the run stays within a few minutes
+    n_inst = min(B, max(threads * 8, 256))
+    pool = ol.CpuPool(n_inst, fs=fs, impl="ref" if kind == "reference" else "oracle", threads=threads)
+    total = PREP_CALLS + (W + K) * cps
+    base = min(n_inst, 64)
+    far, near = synth_streams(base, total * spc, fs, SEED, 40, "echo")
+    reps = (n_inst + base - 1) // base
+    far = np.ascontiguousarray(np.tile(far, (reps, 1))[:n_inst])
+    near = np.ascontiguousarray(np.tile(near, (reps, 1))[:n_inst])
+    c0 = (PREP_CALLS + W * cps) * spc
+    pool.run(np.ascontiguousarray(far[:, :c0]), np.ascontiguousarray(near[:, :c0]), samples_per_call=spc)
+    _, acc, secs = pool.run(np.ascontiguousarray(far[:, c0:]), np.ascontiguousarray(near[:, c0:]), samples_per_call=spc)
+    pool.close()
+    blocks = n_inst * K * cps * spc / 64.0
+    value = blocks / secs
+    cpu = {"value": value, "unit": "blocks/s", "cores": threads, "kind": kind,
+           "sample": f"{n_inst} of {B} instances x {K * cps} steady-state calls, {threads} threads"}
+    print(json.dumps({
+        "impl": "reference", "metric": "AECM blocks/sec (64-sample, 16 kHz) across batch; bit-exact",
+        "value": value, "unit": "blocks/s", "n_gpus": args.gpus, "steps": K, "warmup": W,
+        "ms_per_step": secs * 1e3 / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "int16/int32 Q-format", "data": "synthetic",
+        "config": {"workload": f"batch={B} AecmCore instances per GPU, {fs} Hz, synthetic echo, cng=1 echoMode=3, "
+                               f"msInSndCardBuf=40, steady state (startupState=2)",
+                   "step": f"{cps} 10 ms call(s) (BufferFarend+Process) per instance", "batch_per_gpu": B,
+                   "calls_per_step": cps, "cpu_sample_instances": n_inst},
+        "cpu_baseline": cpu,
+        "e2e": {"value": value, "unit": "blocks/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "return_codes_or": int(acc)}))
+
+
+if __name__ == "__main__":
+    a = parse_args()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_ours(a)

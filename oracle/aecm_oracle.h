@@ -159,6 +159,15 @@ int oracle_run_streams(const OracleRunConfig *cfg, int impl, const char *ref_lib
                        const int16_t *far, const int16_t *near_noisy, const int16_t *near_clean,
                        const int16_t *ms, int16_t *out, int32_t *ret_or, double *seconds);
 
+/* persistent pool (state survives across runs): warm up once, then time steady-state calls */
+typedef struct OraclePool OraclePool;
+OraclePool *oracle_pool_create(int impl, const char *ref_lib_path, int n, int fs, int cng_mode, int echo_mode,
+                               int threads);
+/* runs n_calls x (BufferFarend + Process) on every instance; returns the OR of all return codes */
+int oracle_pool_run(OraclePool *p, const int16_t *far, const int16_t *near_noisy, const int16_t *near_clean,
+                    int16_t *out, int64_t row_stride, int spc, int n_calls, int ms, double *seconds);
+void oracle_pool_free(OraclePool *p);
+
 #ifdef __cplusplus
 }
 #endif

@@ -59,6 +59,13 @@ def oracle():
         lib.oracle_sqrt_floor.restype = C.c_int32
         lib.oracle_sqrt_floor.argtypes = [C.c_int32]
         lib.oracle_real_fft128_inverse.restype = C.c_int
+        lib.oracle_pool_create.restype = C.c_void_p
+        lib.oracle_pool_create.argtypes = [C.c_int, C.c_char_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]
+        lib.oracle_pool_run.restype = C.c_int
+        lib.oracle_pool_run.argtypes = [C.c_void_p] + [C.c_void_p] * 4 + [C.c_int64, C.c_int, C.c_int, C.c_int,
+                                                                           C.POINTER(C.c_double)]
+        lib.oracle_pool_free.restype = None
+        lib.oracle_pool_free.argtypes = [C.c_void_p]
         _lib = lib
     return _lib
 
@@ -231,3 +238,34 @@ def compare_states(dev, orc: OracleState, use_clean=False):
               "last_delay_diff", "time_for_delay_change", "delay_change", "wrapper_known_delay"):
         chk(f, getattr(S, f), getattr(orc, f))
     return bad
+
+
+class CpuPool:
+    """Persistent multi-threaded CPU instances (oracle or reference library) for benchmarking."""
+
+    def __init__(self, n, fs=16000, impl="ref", cng_mode=1, echo_mode=3, threads=None):
+        self.lib = oracle()
+        self.n, self.fs, self.impl = n, fs, impl
+        self.threads = threads or (os.cpu_count() or 1)
+        path = None
+        if impl == "ref":
+            if ref_path() is None:
+                raise FileNotFoundError(REF_SO)
+            path = ref_path().encode()
+        self.h = self.lib.oracle_pool_create(1 if impl == "ref" else 0, path, n, fs, cng_mode, echo_mode, self.threads)
+        if not self.h:
+            raise RuntimeError("oracle_pool_create failed")
+
+    def run(self, far, near, clean=None, samples_per_call=160, ms=40):
+        """far/near: [n, T] int16 C-contiguous; returns (out, or_of_return_codes, seconds)."""
+        assert far.flags["C_CONTIGUOUS"] and near.flags["C_CONTIGUOUS"] and far.shape[0] == self.n
+        out = np.empty_like(near)
+        secs = C.c_double(0)
+        acc = self.lib.oracle_pool_run(self.h, _ptr(far), _ptr(near), _ptr(clean), _ptr(out), far.shape[1],
+                                       samples_per_call, far.shape[1] // samples_per_call, ms, C.byref(secs))
+        return out, acc, secs.value
+
+    def close(self):
+        if self.h:
+            self.lib.oracle_pool_free(self.h)
+            self.h = None

@@ -1,0 +1,68 @@
+"""The C-ABI library loads and exports every symbol the public headers declare (no compute, no GPU needed)."""
+import ctypes
+import os
+import re
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def declared_functions(header):
+    src = open(os.path.join(ROOT, "include", header)).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b((?:WebRtcAecm|AecmB200)_\w+)\s*\(", src)))
+
+
+def test_every_declared_symbol_is_exported():
+    from webrtc_aecm_b200 import api
+
+    lib = ctypes.CDLL(api.library_path())
+    names = declared_functions("echo_control_mobile.h") + declared_functions("aecm_b200.h")
+    assert len(names) >= 30
+    missing = [n for n in names if not hasattr(lib, n)]
+    assert not missing, missing
+
+
+def test_reference_symbol_set_is_complete():
+    # the ten entry points of the reference's aecm/echo_control_mobile.h:46-202
+    want = {"WebRtcAecm_Create", "WebRtcAecm_Free", "WebRtcAecm_Init", "WebRtcAecm_BufferFarend",
+            "WebRtcAecm_GetBufferFarendError", "WebRtcAecm_Process", "WebRtcAecm_set_config",
+            "WebRtcAecm_InitEchoPath", "WebRtcAecm_GetEchoPath", "WebRtcAecm_echo_path_size_bytes"}
+    assert want == set(declared_functions("echo_control_mobile.h"))
+
+
+def test_state_mirror_and_constants():
+    from webrtc_aecm_b200 import api
+
+    L = api.lib()  # asserts sizeof(InstanceState) == AecmB200_StateBytes()
+    assert L.WebRtcAecm_echo_path_size_bytes() == 130
+    assert L.AecmB200_StateBytes() % 16 == 0
+
+
+def test_host_side_argument_errors_need_no_gpu():
+    from webrtc_aecm_b200 import api
+
+    L = api.lib()
+    # NULL instance / batch -> -1, as in the reference (echo_control_mobile.cc:146-148, 200-201, 252-254)
+    assert L.WebRtcAecm_Init(None, 16000) == -1
+    assert L.WebRtcAecm_BufferFarend(None, None, 160) == -1
+    assert L.WebRtcAecm_Process(None, None, None, None, 160, 0) == -1
+    assert L.WebRtcAecm_set_config(None, api.AecmConfig(1, 3)) == -1
+    assert L.WebRtcAecm_GetEchoPath(None, None, 130) == -1
+    assert L.AecmB200_Init(None, 0, 1, 16000) == -1
+    assert L.AecmB200_ProcessStream(None, None) == -1
+    L.WebRtcAecm_Free(None)  # no-op, echo_control_mobile.cc:122-124
+    L.AecmB200_Free(None)
+
+
+def test_product_does_not_reference_the_oracle():
+    bad = []
+    for dirpath, _, files in os.walk(os.path.join(ROOT, "webrtc_aecm_b200")):
+        for f in files:
+            if f.endswith((".c", ".cu", ".h", ".cuh", ".py", "Makefile")):
+                text = open(os.path.join(dirpath, f), errors="ignore").read()
+                if re.search(r"oracle/|aecm_oracle|oracle_lib|libaecm_ref", text):
+                    bad.append(os.path.join(dirpath, f))
+    for f in ("include/aecm_b200.h", "include/echo_control_mobile.h"):
+        if re.search(r"oracle", open(os.path.join(ROOT, f)).read()):
+            bad.append(f)
+    assert not bad, bad

@@ -1,0 +1,109 @@
+"""The reference's ten scalar symbols served by the GPU engine: error codes and bit-exact streaming."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+import oracle_lib as ol
+from webrtc_aecm_b200.synth import synth_streams
+
+pytestmark = pytest.mark.gpu
+
+
+def P(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def test_scalar_api_error_codes_follow_the_reference():
+    from webrtc_aecm_b200 import api
+
+    L = api.scalar_api()
+    h = L.WebRtcAecm_Create()
+    assert h
+    z = np.zeros(160, dtype=np.int16)
+    # un-initialised: echo_control_mobile.cc:206, 264, 417, 496, 521
+    assert L.WebRtcAecm_BufferFarend(h, P(z), 160) == 12002
+    assert L.WebRtcAecm_GetBufferFarendError(h, P(z), 160) == 12002
+    assert L.WebRtcAecm_Process(h, P(z), None, P(z), 160, 0) == 12002
+    assert L.WebRtcAecm_set_config(h, api.AecmConfig(1, 3)) == 12002
+    path = np.zeros(65, dtype=np.int16)
+    assert L.WebRtcAecm_GetEchoPath(h, P(path), 130) == 12002
+    assert L.WebRtcAecm_InitEchoPath(h, P(path), 130) == 12002
+    assert L.WebRtcAecm_Init(h, 44100) == 12004
+    assert L.WebRtcAecm_Init(h, 16000) == 0
+    assert L.WebRtcAecm_BufferFarend(h, None, 160) == 12003
+    assert L.WebRtcAecm_BufferFarend(h, P(z), 100) == 12004
+    assert L.WebRtcAecm_GetBufferFarendError(h, P(z), 160) == 0
+    assert L.WebRtcAecm_Process(h, None, None, P(z), 160, 0) == 12003
+    assert L.WebRtcAecm_Process(h, P(z), None, None, 160, 0) == 12003
+    assert L.WebRtcAecm_Process(h, P(z), None, P(z), 128, 0) == 12004
+    assert L.WebRtcAecm_set_config(h, api.AecmConfig(2, 3)) == 12004
+    assert L.WebRtcAecm_set_config(h, api.AecmConfig(1, 5)) == 12004
+    assert L.WebRtcAecm_set_config(h, api.AecmConfig(1, 1)) == 0
+    assert L.WebRtcAecm_Process(h, P(z), None, P(z), 160, -1) == 12100
+    assert L.WebRtcAecm_Process(h, P(z), None, P(z), 160, 501) == 12100
+    assert L.WebRtcAecm_GetEchoPath(h, P(path), 130) == 0
+    assert path[0] == 2040 and path[64] == 3153
+    assert L.WebRtcAecm_GetEchoPath(h, P(path), 128) == 12004
+    assert L.WebRtcAecm_InitEchoPath(h, None, 130) == 12003
+    assert L.WebRtcAecm_echo_path_size_bytes() == 130
+    L.WebRtcAecm_Free(h)
+    h2 = L.WebRtcAecm_Create()  # a recycled slot starts un-initialised again
+    assert L.WebRtcAecm_BufferFarend(h2, P(z), 160) == 12002
+    L.WebRtcAecm_Free(h2)
+
+
+@pytest.mark.parametrize("fs", [8000, 16000])
+def test_scalar_api_stream_like_main_cc(fs):
+    """The loop of main.cc:128-144 (echoMode 1, CNG on, ms 40), in place like main.cc:141, vs the oracle."""
+    from webrtc_aecm_b200 import api
+
+    L = api.scalar_api()
+    spc = fs // 100
+    calls = 150
+    far, near = synth_streams(2, calls * spc, fs, seed=31)
+    want, ret, _ = ol.run_streams(far, near, fs=fs, impl="oracle", echo_mode=1)
+    hs = [L.WebRtcAecm_Create() for _ in range(2)]
+    got = near.copy()
+    for i, h in enumerate(hs):
+        assert L.WebRtcAecm_Init(h, fs) == 0
+        assert L.WebRtcAecm_set_config(h, api.AecmConfig(1, 1)) == 0
+    for c in range(calls):
+        for i, h in enumerate(hs):
+            f = np.ascontiguousarray(far[i, c * spc:(c + 1) * spc])
+            buf = got[i, c * spc:(c + 1) * spc]
+            assert L.WebRtcAecm_BufferFarend(h, P(f), spc) == 0
+            assert L.WebRtcAecm_Process(h, P(buf), None, P(buf), spc, 40) == 0  # in place
+    np.testing.assert_array_equal(got, want)
+    for h in hs:
+        L.WebRtcAecm_Free(h)
+
+
+def test_echo_path_round_trip_matches_oracle():
+    from webrtc_aecm_b200 import api
+
+    L = api.scalar_api()
+    fs, spc, calls = 16000, 160, 80
+    far, near = synth_streams(1, calls * spc, fs, seed=9)
+    path = (np.arange(65) * 37 % 4000 + 100).astype(np.int16)
+    lib = ol.oracle()
+    o = ol.OracleInstance(fs)
+    assert lib.oracle_aecm_init_echo_path(o.h, path.ctypes.data_as(C.c_void_p), 130) == 0
+    h = L.WebRtcAecm_Create()
+    assert L.WebRtcAecm_Init(h, fs) == 0
+    assert L.WebRtcAecm_InitEchoPath(h, P(path), 130) == 0
+    for c in range(calls):
+        f = np.ascontiguousarray(far[0, c * spc:(c + 1) * spc])
+        n = np.ascontiguousarray(near[0, c * spc:(c + 1) * spc])
+        out = np.zeros_like(n)
+        assert L.WebRtcAecm_BufferFarend(h, P(f), spc) == 0
+        assert L.WebRtcAecm_Process(h, P(n), None, P(out), spc, 40) == 0
+        o.buffer_farend(f)
+        _, want = o.process(n, None, 40)
+        np.testing.assert_array_equal(out, want)
+    got = np.zeros(65, dtype=np.int16)
+    wantp = np.zeros(65, dtype=np.int16)
+    assert L.WebRtcAecm_GetEchoPath(h, P(got), 130) == 0
+    assert lib.oracle_aecm_get_echo_path(o.h, wantp.ctypes.data_as(C.c_void_p), 130) == 0
+    np.testing.assert_array_equal(got, wantp)
+    L.WebRtcAecm_Free(h)

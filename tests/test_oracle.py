@@ -1,0 +1,124 @@
+"""Pins the CPU oracle (oracle/aecm_oracle.c): against the committed golden fixtures generated from the
+unmodified reference (tests/golden/, made by tools/make_golden.py) and, when oracle/_ref is present, against
+the reference library itself.  CPU only."""
+import ctypes as C
+import json
+import os
+
+import numpy as np
+import pytest
+
+import oracle_lib as ol
+from cases import CASES, make_inputs
+from webrtc_aecm_b200.shard import stream_checksum
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+STREAMS = json.load(open(os.path.join(GOLD, "streams.json")))["cases"]
+VEC = np.load(os.path.join(GOLD, "vectors.npz"))
+
+
+def run_case(case, impl):
+    far, near, clean, ms = make_inputs(case)
+    out, ret, _ = ol.run_streams(far, near, fs=case["fs"], samples_per_call=case["spc"], impl=impl, clean=clean, ms=ms,
+                                 cng_mode=case["cng"], echo_mode=case["echo_mode"], skip_far_every=case["skip_far_every"])
+    return far, near, out, ret
+
+
+@pytest.mark.parametrize("case", CASES, ids=[c["name"] for c in CASES])
+def test_oracle_matches_golden_streams(case):
+    far, near, out, ret = run_case(case, "oracle")
+    g = STREAMS[case["name"]]
+    assert stream_checksum(np.concatenate([far, near])) == g["inputs_sha256"], "synthetic inputs drifted"
+    assert list(out.shape) == g["shape"]
+    assert [int(r) for r in ret] == g["ret_or"]
+    assert stream_checksum(out) == g["sha256"]
+    key = "out__" + case["name"]
+    if key in VEC.files:
+        np.testing.assert_array_equal(out, VEC[key])
+
+
+@pytest.mark.skipif(ol.ref_path() is None, reason="oracle/_ref/libaecm_ref.so not built")
+@pytest.mark.parametrize("case", CASES[::3], ids=[c["name"] for c in CASES[::3]])
+def test_oracle_matches_reference_library(case):
+    _, _, out, ret = run_case(case, "oracle")
+    _, _, ref_out, ref_ret = run_case(case, "ref")
+    np.testing.assert_array_equal(out, ref_out)
+    np.testing.assert_array_equal(ret, ref_ret)
+
+
+def test_fft_forward_known_answers():
+    lib = ol.oracle()
+    fin, fout = VEC["fft_fwd_in"], VEC["fft_fwd_out"]
+    got = np.zeros_like(fout)
+    for i in range(len(fin)):
+        lib.oracle_real_fft128_forward(fin[i].ctypes.data_as(C.c_void_p), got[i].ctypes.data_as(C.c_void_p))
+    np.testing.assert_array_equal(got, fout)
+
+
+def test_fft_inverse_known_answers_and_scale():
+    lib = ol.oracle()
+    iin, iout, iscale = VEC["fft_inv_in"], VEC["fft_inv_out"], VEC["fft_inv_scale"]
+    got = np.zeros_like(iout)
+    scale = np.zeros_like(iscale)
+    for i in range(len(iin)):
+        scale[i] = lib.oracle_real_fft128_inverse(iin[i].ctypes.data_as(C.c_void_p), got[i].ctypes.data_as(C.c_void_p))
+    np.testing.assert_array_equal(scale, iscale)
+    np.testing.assert_array_equal(got, iout)
+    assert len(set(iscale.tolist())) >= 4 and iscale.min() == 0  # the vectors exercise the block-floating scaling
+
+
+def test_sqrt_floor_and_lcg_known_answers():
+    lib = ol.oracle()
+    got = np.array([lib.oracle_sqrt_floor(int(v)) for v in VEC["sqrt_in"]], dtype=np.int32)
+    np.testing.assert_array_equal(got, VEC["sqrt_out"])
+    for s, want, after in zip(VEC["rand_seed"], VEC["rand_out"], VEC["rand_seed_after"]):
+        buf = np.zeros(64, dtype=np.int16)
+        seed = C.c_uint32(int(s))
+        lib.oracle_rand_u_array(buf.ctypes.data_as(C.c_void_p), 64, C.byref(seed))
+        np.testing.assert_array_equal(buf, want)
+        assert seed.value == int(after)
+
+
+def test_error_codes_and_call_protocol():
+    lib = ol.oracle()
+    h = lib.oracle_aecm_create()
+    z = np.zeros(160, dtype=np.int16)
+    p = z.ctypes.data_as(C.c_void_p)
+    # un-initialised instance (echo_control_mobile.cc:206, 264, 417)
+    assert lib.oracle_aecm_buffer_farend(h, p, 160) == 12002
+    assert lib.oracle_aecm_process(h, p, None, p, 160, 0) == 12002
+    assert lib.oracle_aecm_set_config(h, 1, 3) == 12002
+    assert lib.oracle_aecm_init(h, 44100) == 12004
+    assert lib.oracle_aecm_init(h, 16000) == 0
+    assert lib.oracle_aecm_buffer_farend(h, None, 160) == 12003
+    assert lib.oracle_aecm_buffer_farend(h, p, 100) == 12004
+    assert lib.oracle_aecm_process(h, None, None, p, 160, 0) == 12003
+    assert lib.oracle_aecm_process(h, p, None, None, 160, 0) == 12003
+    assert lib.oracle_aecm_process(h, p, None, p, 128, 0) == 12004
+    assert lib.oracle_aecm_set_config(h, 2, 3) == 12004
+    assert lib.oracle_aecm_set_config(h, 1, 5) == 12004
+    assert lib.oracle_aecm_process(h, p, None, p, 160, -1) == 12100  # warning, still processed
+    assert lib.oracle_aecm_process(h, p, None, p, 160, 501) == 12100
+    path = np.zeros(65, dtype=np.int16)
+    assert lib.oracle_aecm_get_echo_path(h, path.ctypes.data_as(C.c_void_p), 130) == 0
+    assert path[0] == 2040 and path[64] == 3153  # kChannelStored16kHz, aecm_core.cc:37-43
+    assert lib.oracle_aecm_get_echo_path(h, path.ctypes.data_as(C.c_void_p), 128) == 12004
+    assert lib.oracle_aecm_init_echo_path(h, None, 130) == 12003
+    lib.oracle_aecm_free(h)
+
+
+def test_startup_gate_and_output_lag():
+    """calls 0-5 are pass-through (ECstartup clears inside call 5); afterwards the near end
+    reaches the output with a lag of 112 samples when the far end is silent and CNG is off."""
+    fs, spc, calls = 16000, 160, 40
+    rng = np.random.default_rng(3)
+    near = rng.integers(-3000, 3000, size=(1, calls * spc)).astype(np.int16)
+    far = np.zeros_like(near)
+    out, ret, _ = ol.run_streams(far, near, fs=fs, impl="oracle", cng_mode=0)
+    assert not ret.any()
+    np.testing.assert_array_equal(out[0, :6 * spc], near[0, :6 * spc])
+    assert not np.array_equal(out[0, 6 * spc:7 * spc], near[0, 6 * spc:7 * spc])
+    seg = slice(20 * spc, 30 * spc)
+    err = {lag: np.abs(out[0, seg].astype(int) - near[0, seg.start - lag:seg.stop - lag].astype(int)).mean()
+           for lag in (0, 64, 96, 112, 128)}
+    assert min(err, key=err.get) == 112 and err[112] < 0.05 * err[0]

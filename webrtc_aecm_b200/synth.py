@@ -86,3 +86,70 @@ def synth_streams(n_instances: int, n_samples: int, fs: int = 16000, seed: int =
         near = np.clip(echo + nnoise, -32768, 32767)
         far = far_full[:, max_d:]
         return far.astype(np.int16), near.astype(np.int16)
+
+
+# ---------------------------------------------------------------------------------------------------
+# the same generator on a torch device (bit-identical to synth_streams; used by bench.py to fill HBM
+# with large batches without a host round trip).  All arithmetic is int64 with explicit 32-bit masks.
+# ---------------------------------------------------------------------------------------------------
+def _t_hash32(x):
+    M = 0xFFFFFFFF
+    x = x & M
+    x = x ^ (x >> 16)
+    x = (x * 0x7FEB352D) & M
+    x = x ^ (x >> 15)
+    x = (x * 0x846CA68B) & M
+    x = x ^ (x >> 16)
+    return x
+
+
+def synth_streams_torch(n_instances: int, n_samples: int, fs: int = 16000, seed: int = 0xAEC0, delay_ms=40,
+                        kind: str = "echo", first_instance: int = 0, first_sample: int = 0, device="cuda"):
+    """torch twin of :func:`synth_streams`; returns (far, near) int16 tensors on ``device``."""
+    import torch
+
+    M = 0xFFFFFFFF
+    dev = torch.device(device)
+    i64 = torch.int64
+    inst = (torch.arange(n_instances, dtype=i64, device=dev) + first_instance)[:, None]
+    delay = torch.as_tensor(delay_ms, dtype=i64, device=dev).expand(n_instances).clone()[:, None] * (fs // 1000)
+    max_d = int(delay.max().item()) + 4
+    t = (torch.arange(-max_d, n_samples, dtype=i64, device=dev) + first_sample)[None, :]
+    tu = t & M  # uint32 view of possibly negative sample indices
+    instu = inst & M
+    seg = torch.div(t, fs // 4, rounding_mode="floor")
+    amp_tab = torch.as_tensor((_AMP_STRESS if kind == "stress" else _AMP_ECHO), dtype=i64, device=dev)
+    sel = _t_hash32(((instu * 0x632BE5AB) & M) ^ (((seg & M) * 0x2545F491) & M) ^ (seed & M))
+    amp = amp_tab[(sel >> 7) % amp_tab.numel()]
+
+    def noise16(sd, tt, salt):
+        key = (sd & M) ^ ((instu * 0x9E3779B9) & M) ^ (((tt & M) * 0x85EBCA6B) & M) ^ salt
+        return (_t_hash32(key) >> 16) - 32768
+
+    raw = noise16(seed, tu, 0x1234567)
+    lp = raw.clone()
+    lp[:, 1:] = (raw[:, 1:] + raw[:, :-1]) >> 1
+    far_full = torch.clamp((lp * amp) >> 15, -32768, 32767)
+    far_full = torch.where(t.expand_as(far_full) < 0, torch.zeros_like(far_full), far_full)
+
+    idx = torch.arange(n_samples, dtype=i64, device=dev)[None, :] + max_d
+    g = 64 + (_t_hash32(((instu * 0x27D4EB2F) & M) + (seed & 0xFFFF)) % 448)
+    e0 = torch.gather(far_full, 1, idx - delay)
+    e1 = torch.gather(far_full, 1, idx - delay - 1)
+    e3 = torch.gather(far_full, 1, idx - delay - 3)
+    echo = (g * e0 + (g >> 1) * e1 - (g >> 2) * e3) >> 8
+
+    tn = t[:, max_d:]
+    nseg = torch.div(tn, fs // 2, rounding_mode="floor")
+    nsel = _t_hash32(((instu * 0x9E3779B1) & M) ^ (((nseg & M) * 0x7F4A7C15) & M) ^ ((seed >> 3) & M))
+    ntab = torch.as_tensor([0, 0, 0, 1, 3, 300, 32767, 50000] if kind == "stress" else [0, 3, 30, 100, 300, 300, 4000, 100],
+                           dtype=i64, device=dev)
+    namp = ntab[(nsel >> 9) % ntab.numel()]
+    nnoise = (noise16(seed ^ 0x5bd1e995, tn, 0x7654321) * namp) >> 15
+    if kind == "stress":
+        mute = ((nsel >> 3) % 5) == 0
+        echo = torch.where(mute, torch.zeros_like(echo), echo)
+        nnoise = torch.where(mute, torch.zeros_like(nnoise), nnoise)
+    near = torch.clamp(echo + nnoise, -32768, 32767)
+    far = far_full[:, max_d:]
+    return far.to(torch.int16).contiguous(), near.to(torch.int16).contiguous()
