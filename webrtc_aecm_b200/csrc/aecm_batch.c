@@ -264,6 +264,13 @@ static int grow_planes(AecmB200Batch *b, size_t samples, int need_clean) {
     return 0;
 }
 
+/* plane copy: one flat DMA when the host rows are dense, a pitched copy otherwise */
+static cudaError_t copy_plane(void *dst, size_t dpitch, const void *src, size_t spitch, size_t width, size_t rows,
+                              enum cudaMemcpyKind kind, cudaStream_t s) {
+    if (dpitch == width && spitch == width) return cudaMemcpyAsync(dst, src, width * rows, kind, s);
+    return cudaMemcpy2DAsync(dst, dpitch, src, spitch, width, rows, kind, s);
+}
+
 int32_t AecmB200_ProcessStream(AecmB200Batch *b, const AecmB200StreamArgs *h) {
     AecmB200StreamArgs d;
     size_t width, rows, pitch_src, pitch_dst;
@@ -284,15 +291,15 @@ int32_t AecmB200_ProcessStream(AecmB200Batch *b, const AecmB200StreamArgs *h) {
     d.farend = d.nearendNoisy = d.nearendClean = NULL;
     d.out = NULL;
     if (h->farend) {
-        CU(b, cudaMemcpy2DAsync(b->d_far, pitch_dst, h->farend, pitch_src, pitch_dst, rows, cudaMemcpyHostToDevice, b->stream));
+        CU(b, copy_plane(b->d_far, pitch_dst, h->farend, pitch_src, pitch_dst, rows, cudaMemcpyHostToDevice, b->stream));
         d.farend = b->d_far;
     }
     if (h->nearendNoisy) {
-        CU(b, cudaMemcpy2DAsync(b->d_near, pitch_dst, h->nearendNoisy, pitch_src, pitch_dst, rows, cudaMemcpyHostToDevice, b->stream));
+        CU(b, copy_plane(b->d_near, pitch_dst, h->nearendNoisy, pitch_src, pitch_dst, rows, cudaMemcpyHostToDevice, b->stream));
         d.nearendNoisy = b->d_near;
         d.out = b->d_out;
         if (h->nearendClean) {
-            CU(b, cudaMemcpy2DAsync(b->d_clean, pitch_dst, h->nearendClean, pitch_src, pitch_dst, rows, cudaMemcpyHostToDevice, b->stream));
+            CU(b, copy_plane(b->d_clean, pitch_dst, h->nearendClean, pitch_src, pitch_dst, rows, cudaMemcpyHostToDevice, b->stream));
             d.nearendClean = b->d_clean;
         }
     }
@@ -316,7 +323,7 @@ int32_t AecmB200_ProcessStream(AecmB200Batch *b, const AecmB200StreamArgs *h) {
     rc = AecmB200_ProcessStreamDevice(b, &d);
     if (rc) return rc;
     if (h->nearendNoisy)
-        CU(b, cudaMemcpy2DAsync(h->out, pitch_src, b->d_out, pitch_dst, pitch_dst, rows, cudaMemcpyDeviceToHost, b->stream));
+        CU(b, copy_plane(h->out, pitch_src, b->d_out, pitch_dst, pitch_dst, rows, cudaMemcpyDeviceToHost, b->stream));
     return copy_status_out(b, h->status, h->count);
 }
 

@@ -13,6 +13,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include "aecm_fft.cuh"
 #include "aecm_state.h"
 #include "aecm_tables.h"
 
@@ -52,18 +53,19 @@ constexpr LcgTable make_lcg_table() {
 __device__ const LcgTable kLcgJump = make_lcg_table();
 
 struct CtaTables {
-    uint32_t twiddle[64];
+    int2 tw[64];           // FFT twiddles, entry t: (S[8t+256], S[8t]) of the reference's sine table, sign-extended
+    int4 lane_w[32];       // aecm_fft::LaneWords per lane
+    int4 lane_b[32];       // aecm_fft::LaneBins per lane
     uint32_t cossin[360];
     uint32_t lcg_mul[64], lcg_add[64];
     int16_t hann[66];
 };
 
 struct __align__(16) WarpScratch {
-    uint32_t fft[128];     // packed complex int16: re in the low half, im in the high half
+    uint32_t fft[256];     // two 128-word transpose tiles of the register FFT (packed complex int16)
     uint32_t dfw[68];      // near (or clean) spectrum after the sign flip of aecm_core_c.cc:188-190
     int32_t echo_est[68];
     uint16_t xfa[72], dfa_noisy[72], dfa_clean[72], far_row[72];
-    int16_t out_blk[64];
 };
 
 struct Ctx {
@@ -136,107 +138,50 @@ __device__ __forceinline__ int wrap_add(int base, int k, int cap) {  // (base + 
 __device__ __forceinline__ int brev7(int n) { return (int)(__brev((unsigned)n) >> 25); }
 
 // ------------------------------------------------------------------------------------------------
-// 128-point fixed-point complex FFT / IFFT on a warp (complex_fft.c:241-491, mode 1)
-// Data lives in shared memory as 128 packed words in bit-reversed input order; stage s pairs words that
-// differ in bit s; each lane executes two butterflies per stage.
+// TimeToFrequencyDomain (aecm_core_c.cc:261-365) incl. WindowAndFFT (:166-191) for NS signals at once
+// (far + near share twiddles, addresses and instruction-level parallelism).  The transform itself is the
+// register-resident warp FFT of aecm_fft.cuh.  old64[n]: previous block half in shared memory; new_at(n, k):
+// k-th new sample of signal n.  Writes 65 magnitudes per signal, optionally the packed complex bins (sign
+// convention after the conjugation of :188-190), the magnitude sums and the dynamic-Q shifts.
 // ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void fft128_forward(uint32_t *buf, const uint32_t *tw, int lane) {
-#pragma unroll
-    for (int s = 0; s < 7; s++) {
-        const int half = 1 << s;
-#pragma unroll
-        for (int h = 0; h < 2; h++) {
-            const int b = lane + 32 * h;
-            const int m = b & (half - 1);
-            const int i = ((b >> s) << (s + 1)) | m;
-            const int j = i + half;
-            const uint32_t w = tw[m << (6 - s)];
-            const int wr = lo16(w), wi = -hi16(w);  // complex_fft.c:303-304
-            const uint32_t cj = buf[j], ci = buf[i];
-            const int xr = lo16(cj), xi = hi16(cj);
-            const int tr = (wr * xr - wi * xi + 1) >> 1;  // :332-338
-            const int ti = (wr * xi + wi * xr + 1) >> 1;
-            const int qr = lo16(ci) * 16384 + 16384;      // :340-341 plus CFFTRND2
-            const int qi = hi16(ci) * 16384 + 16384;
-            buf[j] = pack16((qr - tr) >> 15, (qi - ti) >> 15);  // :343-350
-            buf[i] = pack16((qr + tr) >> 15, (qi + ti) >> 15);
-        }
-        __syncwarp();
-    }
+__device__ __forceinline__ aecm_fft::LaneWords lane_words_of(const Ctx &c) {
+    const int4 v = c.tab->lane_w[c.lane];
+    return aecm_fft::LaneWords{v.x, v.y, v.z, v.w};
 }
 
-// returns the accumulated scale (complex_fft.c:381-396: shift 0/1/2 per stage from the pre-stage peak)
-__device__ __forceinline__ int fft128_inverse(uint32_t *buf, const uint32_t *tw, int lane, int peak) {
-    int scale = 0;
-#pragma unroll
-    for (int s = 0; s < 7; s++) {
-        const int half = 1 << s;
-        const int shift = (peak > 13573) + (peak > 27146);
-        const int rnd = 8192 << shift;
-        scale += shift;
-        int mx = 0;
-#pragma unroll
-        for (int h = 0; h < 2; h++) {
-            const int b = lane + 32 * h;
-            const int m = b & (half - 1);
-            const int i = ((b >> s) << (s + 1)) | m;
-            const int j = i + half;
-            const uint32_t w = tw[m << (6 - s)];
-            const int wr = lo16(w), wi = hi16(w);  // complex_fft.c:437-438
-            const uint32_t cj = buf[j], ci = buf[i];
-            const int xr = lo16(cj), xi = hi16(cj);
-            const int tr = (wr * xr - wi * xi + 1) >> 1;  // :465-470
-            const int ti = (wr * xi + wi * xr + 1) >> 1;
-            const int qr = lo16(ci) * 16384 + rnd;        // :472-473 plus round2
-            const int qi = hi16(ci) * 16384 + rnd;
-            const int sh = shift + 14;
-            const int ar = s16((qr - tr) >> sh), ai = s16((qi - ti) >> sh);  // :475-482
-            const int br = s16((qr + tr) >> sh), bi = s16((qi + ti) >> sh);
-            buf[j] = pack16(ar, ai);
-            buf[i] = pack16(br, bi);
-            mx = max(max(max(abs(ar), abs(ai)), max(abs(br), abs(bi))), mx);
-        }
-        peak = min(__reduce_max_sync(kFull, mx), 32767);  // WebRtcSpl_MaxAbsValueW16 of the next stage's input
-        __syncwarp();
-    }
-    return scale;
-}
-
-// ------------------------------------------------------------------------------------------------
-// TimeToFrequencyDomain (aecm_core_c.cc:261-365) incl. WindowAndFFT (:166-191)
-// old64: previous block half in shared memory; NewAt(k): k-th new sample.  Writes 65 magnitudes, optionally
-// the packed complex bins, returns the dynamic-Q shift; *sum_out = sum of magnitudes.
-// ------------------------------------------------------------------------------------------------
-template <class NewAt>
-__device__ __forceinline__ int time_to_frequency(const Ctx &c, const int16_t *old64, NewAt new_at, uint16_t *mag_out,
-                                                 uint32_t *cplx_out, uint32_t &sum_out) {
+template <int NS, class NewAt>
+__device__ __forceinline__ void time_to_frequency(const Ctx &c, const int16_t *const (&old64)[NS], NewAt new_at,
+                                                  uint16_t *const (&mag_out)[NS], uint32_t *const (&cplx_out)[NS],
+                                                  uint32_t (&sum_out)[NS], int (&q_out)[NS]) {
     const int lane = c.lane;
-    uint32_t *buf = c.sc->fft;
-    int x[4];
-    x[0] = old64[lane];
-    x[1] = old64[lane + 32];
-    x[2] = new_at(lane);
-    x[3] = new_at(lane + 32);
-    int peak = max(max(abs(x[0]), abs(x[1])), max(abs(x[2]), abs(x[3])));
-    peak = min(__reduce_max_sync(kFull, peak), 32767);  // signal_processing_library.cc:154-174
-    const int q = norm_w16(peak);                       // :288-289
+    const int n0 = (int)(__brev((unsigned)lane) >> 27);  // the lane owns time indices n0 + 32k (bit-reversed order)
+    const int w0 = c.tab->hann[n0], w1 = c.tab->hann[n0 + 32], w2 = c.tab->hann[64 - n0], w3 = c.tab->hann[32 - n0];
+    int x[NS][4];
 #pragma unroll
-    for (int k = 0; k < 4; k++) {
-        const int n = lane + 32 * k;
-        const int scaled = s16(x[k] << q);              // :177 / :179
-        const int w = c.tab->hann[n < 64 ? n : 128 - n];
-        buf[brev7(n)] = (uint32_t)(((scaled * w) >> 14) & 0xffff);  // :178 / :180-181, imaginary part 0
+    for (int n = 0; n < NS; n++) {
+        x[n][0] = old64[n][n0];
+        x[n][1] = old64[n][n0 + 32];
+        x[n][2] = new_at(n, n0);
+        x[n][3] = new_at(n, n0 + 32);
+        int peak = max(max(abs(x[n][0]), abs(x[n][1])), max(abs(x[n][2]), abs(x[n][3])));
+        peak = min(__reduce_max_sync(kFull, peak), 32767);  // signal_processing_library.cc:154-174
+        const int q = norm_w16(peak);                       // :288-289
+        q_out[n] = q;
+        x[n][0] = (s16(x[n][0] << q) * w0) >> 14;           // :177-181 (the product always fits int16)
+        x[n][1] = (s16(x[n][1] << q) * w1) >> 14;
+        x[n][2] = (s16(x[n][2] << q) * w2) >> 14;
+        x[n][3] = (s16(x[n][3] << q) * w3) >> 14;
     }
-    __syncwarp();
-    fft128_forward(buf, c.tab->twiddle, lane);
-    uint32_t sum = 0;
+    int bre[NS][3], bim[NS][3];
+    aecm_fft::forward128<NS>(x, c.sc->fft, c.tab->tw, lane_words_of(c), lane, bre, bim);
 #pragma unroll
-    for (int p = 0; p < 3; p++) {
-        const int i = lane + 32 * p;
-        if (i < AECM_BINS) {
-            const uint32_t v = buf[i];
-            const int re = lo16(v);
-            const int im = (i == 0 || i == 64) ? 0 : s16(-hi16(v));  // :188-190, :296-297
+    for (int n = 0; n < NS; n++) {
+        uint32_t sum = 0;
+#pragma unroll
+        for (int p = 0; p < 3; p++) {
+            const int i = p < 2 ? lane + 32 * p : 64;
+            const int re = bre[n][p];
+            const int im = (i == 0 || i == 64) ? 0 : s16(-bim[n][p]);  // :188-190, :296-297
             int mag;
             if (re == 0) mag = abs(im);       // :305-308; |-32768| = 32768 as uint16
             else if (im == 0) mag = abs(re);
@@ -244,14 +189,15 @@ __device__ __forceinline__ int time_to_frequency(const Ctx &c, const int16_t *ol
                 const uint32_t e = (uint32_t)(re * re) + (uint32_t)(im * im);  // :350-354 with AddSatW32
                 mag = sqrt_floor((int)min(e, 0x7fffffffu));
             }
-            mag_out[i] = (uint16_t)mag;
-            if (cplx_out) cplx_out[i] = pack16(re, im);
-            sum += (uint32_t)mag;
+            if (p < 2 || lane == 0) {
+                mag_out[n][i] = (uint16_t)mag;
+                if (cplx_out[n]) cplx_out[n][i] = pack16(re, im);
+                sum += (uint32_t)mag;
+            }
         }
+        sum_out[n] = __reduce_add_sync(kFull, sum);
     }
-    sum_out = __reduce_add_sync(kFull, sum);
     __syncwarp();
-    return q;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -314,9 +260,10 @@ __device__ __forceinline__ int process_binary_spectrum(AecmInstanceState *st, ui
 
 // ------------------------------------------------------------------------------------------------
 // one 64-sample block (aecm_core_c.cc:368-711).  Input samples are read from the frame FIFOs in shared
-// memory starting at in_rd / clean_rd; the output block is left in sc->out_blk.
+// memory starting at in_rd / clean_rd; the first out_n samples of the output block are appended to the output
+// FIFO at index out_wr (WebRtc_WriteBuffer of aecm_core.cc:554).
 // ------------------------------------------------------------------------------------------------
-__device__ __noinline__ void process_block(const Ctx &c, int in_rd, int clean_rd, bool use_clean) {
+__device__ __noinline__ void process_block(const Ctx &c, int in_rd, int clean_rd, bool use_clean, int out_wr, int out_n) {
     AecmInstanceState *st = c.st;
     WarpScratch *sc = c.sc;
     AecmScalars &S = st->s;
@@ -325,12 +272,25 @@ __device__ __noinline__ void process_block(const Ctx &c, int in_rd, int clean_rd
     if (S.startup_state < 2) S.startup_state = (S.tot_count >= kConvLen) + (S.tot_count >= 2 * kConvLen);  // :420-424
 
     // ---- analysis: far, near (noisy) and optionally near (clean), :428-464 ----
-    uint32_t xfa_sum, dfa_noisy_sum, dfa_clean_sum;
-    const int far_q = time_to_frequency(
-        c, st->x_old, [&](int k) { return (int)st->frm_far[wrap_add(in_rd, k, AECM_FRM_RING)]; }, sc->xfa, nullptr, xfa_sum);
-    const int q_noisy = time_to_frequency(
-        c, st->d_noisy_old, [&](int k) { return (int)st->frm_near[wrap_add(in_rd, k, AECM_FRM_RING)]; }, sc->dfa_noisy,
-        sc->dfw, dfa_noisy_sum);
+    uint32_t dfa_noisy_sum;
+    int far_q, q_noisy;
+    {
+        const int16_t *const olds[2] = {st->x_old, st->d_noisy_old};
+        uint16_t *const mags[2] = {sc->xfa, sc->dfa_noisy};
+        uint32_t *const cplx[2] = {nullptr, sc->dfw};
+        uint32_t sums[2];
+        int qs[2];
+        time_to_frequency<2>(
+            c, olds,
+            [&](int n, int k) {
+                const int idx = wrap_add(in_rd, k, AECM_FRM_RING);
+                return (int)(n == 0 ? st->frm_far[idx] : st->frm_near[idx]);
+            },
+            mags, cplx, sums, qs);
+        far_q = qs[0];
+        q_noisy = qs[1];
+        dfa_noisy_sum = sums[1];
+    }
     S.q_noisy_old = S.q_noisy;
     S.q_noisy = q_noisy;
     const uint16_t *dfa_clean = sc->dfa_noisy;
@@ -338,11 +298,16 @@ __device__ __noinline__ void process_block(const Ctx &c, int in_rd, int clean_rd
         S.q_clean_old = S.q_noisy_old;
         S.q_clean = S.q_noisy;
     } else {
-        const int qc = time_to_frequency(
-            c, st->d_clean_old, [&](int k) { return (int)st->frm_clean[wrap_add(clean_rd, k, AECM_FRM_RING)]; },
-            sc->dfa_clean, sc->dfw, dfa_clean_sum);
+        const int16_t *const olds[1] = {st->d_clean_old};
+        uint16_t *const mags[1] = {sc->dfa_clean};
+        uint32_t *const cplx[1] = {sc->dfw};  // the Wiener gain is applied to the clean spectrum (:458)
+        uint32_t sums[1];
+        int qs[1];
+        time_to_frequency<1>(
+            c, olds, [&](int, int k) { return (int)st->frm_clean[wrap_add(clean_rd, k, AECM_FRM_RING)]; }, mags, cplx,
+            sums, qs);
         S.q_clean_old = S.q_clean;
-        S.q_clean = qc;
+        S.q_clean = qs[0];
         dfa_clean = sc->dfa_clean;
     }
     const int q_clean = S.q_clean, q_clean_old = S.q_clean_old;
@@ -758,28 +723,33 @@ __device__ __noinline__ void process_block(const Ctx &c, int in_rd, int clean_rd
 
     // ---- InverseFFTAndWindow (aecm_core_c.cc:193-246, real_fft.c:74-102) ----
     int peak = 0;
+    {
+        const int4 lb = c.tab->lane_b[lane];  // tile words of bins lane, lane+32 and of their mirrors
+        const int words[2] = {lb.x, lb.y}, mirrors[2] = {lb.z, lb.w};
 #pragma unroll
-    for (int p = 0; p < 3; p++) {
-        const int i = lane + 32 * p;
-        if (i < AECM_BINS) {
-            const int nim = s16(-eim[p]);  // aecm_core_c.cc:206-214
-            sc->fft[brev7(i)] = pack16(ere[p], nim);
-            peak = max(peak, max(abs(ere[p]), abs(nim)));
-            if (i > 0 && i < 64) sc->fft[brev7(128 - i)] = pack16(ere[p], s16(-nim));  // real_fft.c:87-91
+        for (int p = 0; p < 3; p++) {
+            const int i = p < 2 ? lane + 32 * p : 64;
+            if (p < 2 || lane == 0) {
+                const int nim = s16(-eim[p]);  // aecm_core_c.cc:206-214
+                sc->fft[p < 2 ? words[p] : aecm_fft::phys(1)] = pack16(ere[p], nim);  // bin 64 sits at position brev7(64) = 1
+                peak = max(peak, max(abs(ere[p]), abs(nim)));
+                if (p < 2 && i > 0) sc->fft[mirrors[p]] = pack16(ere[p], s16(-nim));  // real_fft.c:87-91
+            }
         }
     }
     peak = min(__reduce_max_sync(kFull, peak), 32767);
     __syncwarp();
-    const int scale = fft128_inverse(sc->fft, c.tab->twiddle, lane, peak);
+    int td[4];
+    const int scale = aecm_fft::inverse128(sc->fft, c.tab->tw, lane_words_of(c), lane, peak, td);
     const int cshift = scale - q_clean;
 #pragma unroll
     for (int h = 0; h < 2; h++) {
         const int i = lane + 32 * h;
         const int w0 = c.tab->hann[i], w1 = c.tab->hann[64 - i];
-        int t32 = s16((lo16(sc->fft[i]) * w0 + 8192) >> 14);  // :219-221
+        int t32 = s16((td[h] * w0 + 8192) >> 14);  // :219-221
         t32 = shift_s32(t32, cshift);
-        sc->out_blk[i] = (int16_t)sat16(t32 + (int)st->out_ola[i]);  // :224-227
-        t32 = (lo16(sc->fft[64 + i]) * w1) >> 14;  // :229-230 (no rounding here)
+        if (i < out_n) st->frm_out[wrap_add(out_wr, i, AECM_FRM_RING)] = (int16_t)sat16(t32 + (int)st->out_ola[i]);  // :224-227
+        t32 = (td[2 + h] * w1) >> 14;  // :229-230 (no rounding here)
         t32 = shift_s32(t32, cshift);
         st->out_ola[i] = (int16_t)sat16(t32);
         // slide the analysis buffers, :239-245
@@ -836,12 +806,11 @@ __device__ __forceinline__ void process_frame(const Ctx &c, int far_idx, int slo
     while (S.frm_in_cnt >= AECM_PART_LEN) {  // :527-555
         const int in_rd = S.frm_in_rd;
         const int clean_rd = S.frm_clean_rd;
-        process_block(c, in_rd, clean_rd, clean80 != nullptr);
-        fifo_move(S.frm_in_rd, S.frm_in_cnt, AECM_FRM_RING, AECM_PART_LEN);
-        if (clean80) fifo_move(S.frm_clean_rd, S.frm_clean_cnt, AECM_FRM_RING, AECM_PART_LEN);
         const int n = min(AECM_PART_LEN, AECM_FRM_RING - S.frm_out_cnt);
         const int wr = wrap_add(S.frm_out_rd, S.frm_out_cnt, AECM_FRM_RING);
-        for (int k = lane; k < n; k += 32) st->frm_out[wrap_add(wr, k, AECM_FRM_RING)] = c.sc->out_blk[k];
+        process_block(c, in_rd, clean_rd, clean80 != nullptr, wr, n);
+        fifo_move(S.frm_in_rd, S.frm_in_cnt, AECM_FRM_RING, AECM_PART_LEN);
+        if (clean80) fifo_move(S.frm_clean_rd, S.frm_clean_cnt, AECM_FRM_RING, AECM_PART_LEN);
         S.frm_out_cnt += n;
         __syncwarp();
     }
@@ -965,21 +934,28 @@ __device__ __forceinline__ int api_process(const Ctx &c, const int16_t *near_noi
 // ------------------------------------------------------------------------------------------------
 struct __align__(16) CtaShared {
     CtaTables tab;
-    uint32_t pad_[2];
+    uint32_t pad_[3];
 };
 
 __device__ __forceinline__ void load_tables(CtaTables *t) {
     for (int k = threadIdx.x; k < 64; k += blockDim.x) {
-        t->twiddle[k] = kAecmTwiddle128[k];
+        const uint32_t w = kAecmTwiddle128[k];
+        t->tw[k] = make_int2(lo16(w), hi16(w));
         t->lcg_mul[k] = kLcgJump.mul[k];
         t->lcg_add[k] = kLcgJump.add[k];
     }
     for (int k = threadIdx.x; k < 360; k += blockDim.x) t->cossin[k] = kAecmCosSinQ13[k];
     for (int k = threadIdx.x; k < 65; k += blockDim.x) t->hann[k] = kAecmSqrtHanningQ14[k];
+    if (threadIdx.x < 32) {
+        const aecm_fft::LaneWords lw = aecm_fft::lane_words(threadIdx.x);
+        const aecm_fft::LaneBins lb = aecm_fft::lane_bins(threadIdx.x);
+        t->lane_w[threadIdx.x] = make_int4(lw.a, lw.b, lw.c, lw.d);
+        t->lane_b[threadIdx.x] = make_int4(lb.k0, lb.k1, lb.m0, lb.m1);
+    }
 }
 
 // shared memory: [CtaShared][kWarpsPerCta x (AecmInstanceState, WarpScratch)]
-__global__ void __launch_bounds__(kWarpsPerCta * 32) aecm_call_kernel(AecmBatchPlanes planes, AecmCallArgs a) {
+__global__ void __launch_bounds__(kWarpsPerCta * 32, 7) aecm_call_kernel(AecmBatchPlanes planes, AecmCallArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     CtaShared *cs = reinterpret_cast<CtaShared *>(smem_raw);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -1177,6 +1153,8 @@ int aecm_cuda_launch_call(const AecmBatchPlanes *p, const AecmCallArgs *a, void 
     const size_t smem = sizeof(CtaShared) + (size_t)kWarpsPerCta * (sizeof(AecmInstanceState) + sizeof(WarpScratch));
     if (!attr_set) {
         cudaError_t e = cudaFuncSetAttribute(aecm_call_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return (int)e;
+        e = cudaFuncSetAttribute(aecm_call_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
         if (e != cudaSuccess) return (int)e;
         attr_set = true;
     }
