@@ -21,6 +21,7 @@ namespace {
 
 constexpr unsigned kFull = 0xffffffffu;
 constexpr int kWarpsPerCta = 4;
+constexpr int kCtasPerSm = 7;  // 28 warps/SM: BASELINE configs[1] (4096 instances) is a single wave on 148 SMs
 
 // ---- algorithm constants, aecm_defines.h:28-85 ----
 constexpr int kConvLen = 512;
@@ -52,26 +53,40 @@ constexpr LcgTable make_lcg_table() {
 }
 __device__ const LcgTable kLcgJump = make_lcg_table();
 
-struct CtaTables {
-    int2 tw[64];           // FFT twiddles, entry t: (S[8t+256], S[8t]) of the reference's sine table, sign-extended
-    int4 lane_w[32];       // aecm_fft::LaneWords per lane
-    int4 lane_b[32];       // aecm_fft::LaneBins per lane
-    uint32_t cossin[360];
-    uint32_t lcg_mul[64], lcg_add[64];
-    int16_t hann[66];
+// Per-lane constant words of the FFT tile layouts (aecm_fft.cuh), built at compile time.  All constant tables
+// stay in global memory and are read through the read-only path: they are a few KB, hit in L1 after first touch,
+// and cost neither shared memory nor a per-launch staging loop.
+struct LaneTables {
+    int4 words[32];  // aecm_fft::LaneWords {a, b, c, d}
+    int4 bins[32];   // aecm_fft::LaneBins {k0, k1, m0, m1}
 };
+constexpr LaneTables make_lane_tables() {
+    LaneTables t{};
+    for (int L = 0; L < 32; L++) {
+        t.words[L] = int4{aecm_fft::phys(4 * L), aecm_fft::phys((L >> 2) * 16 + (L & 3)),
+                          aecm_fft::phys((L >> 4) * 64 + (L & 15)), aecm_fft::phys(L)};
+        t.bins[L] = int4{aecm_fft::phys(aecm_fft::brev7c(L)), aecm_fft::phys(aecm_fft::brev7c(L + 32)),
+                         aecm_fft::phys(aecm_fft::brev7c((128 - L) & 127)), aecm_fft::phys(aecm_fft::brev7c(96 - L))};
+    }
+    return t;
+}
+__device__ const LaneTables kLaneTables = make_lane_tables();
+
+__device__ __forceinline__ const int2 *twiddle_table() { return reinterpret_cast<const int2 *>(kAecmTwiddleCS); }
+__device__ __forceinline__ int hann_q14(int i) { return __ldg(&kAecmSqrtHanningQ14[i]); }
 
 struct __align__(16) WarpScratch {
     uint32_t fft[256];     // two 128-word transpose tiles of the register FFT (packed complex int16)
     uint32_t dfw[68];      // near (or clean) spectrum after the sign flip of aecm_core_c.cc:188-190
     int32_t echo_est[68];
     uint16_t xfa[72], dfa_noisy[72], dfa_clean[72], far_row[72];
+    uint64_t mbar;         // mbarrier of the record's bulk load
+    uint64_t pad_;
 };
 
 struct Ctx {
     AecmInstanceState *st;  // shared-memory copy of the record
     WarpScratch *sc;
-    const CtaTables *tab;
     uint16_t *far_hist;     // this instance's 100 x 66 rows in HBM
     int16_t *far_ring;      // this instance's 4000-sample jitter FIFO in HBM
     int lane;
@@ -145,7 +160,7 @@ __device__ __forceinline__ int brev7(int n) { return (int)(__brev((unsigned)n) >
 // convention after the conjugation of :188-190), the magnitude sums and the dynamic-Q shifts.
 // ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ aecm_fft::LaneWords lane_words_of(const Ctx &c) {
-    const int4 v = c.tab->lane_w[c.lane];
+    const int4 v = __ldg(&kLaneTables.words[c.lane]);
     return aecm_fft::LaneWords{v.x, v.y, v.z, v.w};
 }
 
@@ -155,7 +170,7 @@ __device__ __forceinline__ void time_to_frequency(const Ctx &c, const int16_t *c
                                                   uint32_t (&sum_out)[NS], int (&q_out)[NS]) {
     const int lane = c.lane;
     const int n0 = (int)(__brev((unsigned)lane) >> 27);  // the lane owns time indices n0 + 32k (bit-reversed order)
-    const int w0 = c.tab->hann[n0], w1 = c.tab->hann[n0 + 32], w2 = c.tab->hann[64 - n0], w3 = c.tab->hann[32 - n0];
+    const int w0 = hann_q14(n0), w1 = hann_q14(n0 + 32), w2 = hann_q14(64 - n0), w3 = hann_q14(32 - n0);
     int x[NS][4];
 #pragma unroll
     for (int n = 0; n < NS; n++) {
@@ -167,13 +182,14 @@ __device__ __forceinline__ void time_to_frequency(const Ctx &c, const int16_t *c
         peak = min(__reduce_max_sync(kFull, peak), 32767);  // signal_processing_library.cc:154-174
         const int q = norm_w16(peak);                       // :288-289
         q_out[n] = q;
-        x[n][0] = (s16(x[n][0] << q) * w0) >> 14;           // :177-181 (the product always fits int16)
-        x[n][1] = (s16(x[n][1] << q) * w1) >> 14;
-        x[n][2] = (s16(x[n][2] << q) * w2) >> 14;
-        x[n][3] = (s16(x[n][3] << q) * w3) >> 14;
+        // :177-181; q = NormW16(max|x|) guarantees x << q stays int16, and the Q14 window keeps the product int16
+        x[n][0] = ((x[n][0] << q) * w0) >> 14;
+        x[n][1] = ((x[n][1] << q) * w1) >> 14;
+        x[n][2] = ((x[n][2] << q) * w2) >> 14;
+        x[n][3] = ((x[n][3] << q) * w3) >> 14;
     }
     int bre[NS][3], bim[NS][3];
-    aecm_fft::forward128<NS>(x, c.sc->fft, c.tab->tw, lane_words_of(c), lane, bre, bim);
+    aecm_fft::forward128<NS>(x, c.sc->fft, twiddle_table(), lane_words_of(c), lane, bre, bim);
 #pragma unroll
     for (int n = 0; n < NS; n++) {
         uint32_t sum = 0;
@@ -263,7 +279,7 @@ __device__ __forceinline__ int process_binary_spectrum(AecmInstanceState *st, ui
 // memory starting at in_rd / clean_rd; the first out_n samples of the output block are appended to the output
 // FIFO at index out_wr (WebRtc_WriteBuffer of aecm_core.cc:554).
 // ------------------------------------------------------------------------------------------------
-__device__ __noinline__ void process_block(const Ctx &c, int in_rd, int clean_rd, bool use_clean, int out_wr, int out_n) {
+__device__ __forceinline__ void process_block(const Ctx &c, int in_rd, int clean_rd, bool use_clean, int out_wr, int out_n) {
     AecmInstanceState *st = c.st;
     WarpScratch *sc = c.sc;
     AecmScalars &S = st->s;
@@ -607,15 +623,15 @@ __device__ __noinline__ void process_block(const Ctx &c, int in_rd, int clean_rd
             int z16 = norm_w16(nf);
             int n1, n2, q_diff;
             if (z16 < dq_clean && nf) {  // :556-566
-                n1 = s16(nf << z16);
+                n1 = nf << z16;  // NormW16 shift: stays int16
                 q_diff = z16 - dq_clean;
-                n2 = s16(dfc >> -q_diff);
+                n2 = dfc >> -q_diff;  // uint16 >> (>=1): fits int16
             } else {
-                n1 = dq_clean < 0 ? nf >> -dq_clean : s16(nf << dq_clean);
+                n1 = dq_clean < 0 ? nf >> -dq_clean : nf << dq_clean;  // here dq_clean <= NormW16(nf) (or nf == 0)
                 q_diff = 0;
                 n2 = s16(dfc);
             }
-            n2 = s16(s16((n2 - n1) >> 4) + n1);  // :567-570
+            n2 = s16(((n2 - n1) >> 4) + n1);  // :567-570 (the inner int16 store cannot truncate)
             z16 = norm_w16(n2);
             int nfn;
             if (n2 & (int)(-q_diff > z16)) nfn = 32767;  // :572 (bitwise and of the value with the flag)
@@ -632,7 +648,7 @@ __device__ __noinline__ void process_block(const Ctx &c, int in_rd, int clean_rd
                 const int t32 = (int)shift_u32(ratio, res_diff);
                 if (t32 > kOneQ14) h = 0;
                 else if (t32 < 0) h = kOneQ14;
-                else h = max(s16(kOneQ14 - s16(t32)), 0);
+                else h = kOneQ14 - t32;  // t32 in [0, 2^14]: neither int16 store truncates, never negative
             }
             hnl[p] = h;
             num_pos += (h != 0);
@@ -665,8 +681,8 @@ __device__ __noinline__ void process_block(const Ctx &c, int in_rd, int clean_rd
             if (!(h == kOneQ14 && nlp_gain == kOneQ14)) h = (h * nlp_gain) >> 14;
             hnl[p] = h;
             const uint32_t d = sc->dfw[i];
-            ere[p] = s16((lo16(d) * h + 8192) >> 14);
-            eim[p] = s16((hi16(d) * h + 8192) >> 14);
+            ere[p] = (lo16(d) * h + 8192) >> 14;  // |d| <= 2^15, h <= 2^14: always int16
+            eim[p] = (hi16(d) * h + 8192) >> 14;
         }
     }
 
@@ -705,26 +721,26 @@ __device__ __noinline__ void process_block(const Ctx &c, int in_rd, int clean_rd
                 st->noise_est[i] = ne;
                 st->noise_low_ctr[i] = (uint8_t)lo_c;
                 st->noise_high_ctr[i] = (uint8_t)hi_c;
-                const int noise = s16((s16(kOneQ14 - hnl[p]) * t32) >> 14);
+                const int noise = ((kOneQ14 - hnl[p]) * t32) >> 14;  // in [0, 32767]
                 if (i > 0) {  // :146-163: bin 0 gets no noise, bin 64 only a real part
-                    const uint32_t r = (c.tab->lcg_mul[i - 1] * seed + c.tab->lcg_add[i - 1]) & 0x7fffffffu;
+                    const uint32_t r = (__ldg(&kLcgJump.mul[i - 1]) * seed + __ldg(&kLcgJump.add[i - 1])) & 0x7fffffffu;
                     const int rnd = (int)(r >> 16);
                     const int idx = (359 * rnd) >> 15;
-                    const uint32_t cs = c.tab->cossin[idx];
-                    const int ur = s16((noise * lo16(cs)) >> 13);
-                    const int ui = i < 64 ? s16((-noise * hi16(cs)) >> 13) : 0;
+                    const uint32_t cs = __ldg(&kAecmCosSinQ13[idx]);
+                    const int ur = (noise * lo16(cs)) >> 13;  // |cos|, |sin| <= 2^13: always int16
+                    const int ui = i < 64 ? (-noise * hi16(cs)) >> 13 : 0;
                     ere[p] = sat16(ere[p] + ur);
                     eim[p] = sat16(eim[p] + ui);
                 }
             }
         }
-        S.seed = (c.tab->lcg_mul[63] * seed + c.tab->lcg_add[63]) & 0x7fffffffu;  // 64 draws per block, :143
+        S.seed = (kLcgJump.mul[63] * seed + kLcgJump.add[63]) & 0x7fffffffu;  // 64 draws per block, :143
     }
 
     // ---- InverseFFTAndWindow (aecm_core_c.cc:193-246, real_fft.c:74-102) ----
     int peak = 0;
     {
-        const int4 lb = c.tab->lane_b[lane];  // tile words of bins lane, lane+32 and of their mirrors
+        const int4 lb = __ldg(&kLaneTables.bins[lane]);  // tile words of bins lane, lane+32 and of their mirrors
         const int words[2] = {lb.x, lb.y}, mirrors[2] = {lb.z, lb.w};
 #pragma unroll
         for (int p = 0; p < 3; p++) {
@@ -740,13 +756,13 @@ __device__ __noinline__ void process_block(const Ctx &c, int in_rd, int clean_rd
     peak = min(__reduce_max_sync(kFull, peak), 32767);
     __syncwarp();
     int td[4];
-    const int scale = aecm_fft::inverse128(sc->fft, c.tab->tw, lane_words_of(c), lane, peak, td);
+    const int scale = aecm_fft::inverse128(sc->fft, twiddle_table(), lane_words_of(c), lane, peak, td);
     const int cshift = scale - q_clean;
 #pragma unroll
     for (int h = 0; h < 2; h++) {
         const int i = lane + 32 * h;
-        const int w0 = c.tab->hann[i], w1 = c.tab->hann[64 - i];
-        int t32 = s16((td[h] * w0 + 8192) >> 14);  // :219-221
+        const int w0 = hann_q14(i), w1 = hann_q14(64 - i);
+        int t32 = (td[h] * w0 + 8192) >> 14;  // :219-221 (int16 by the Q14 window)
         t32 = shift_s32(t32, cshift);
         if (i < out_n) st->frm_out[wrap_add(out_wr, i, AECM_FRM_RING)] = (int16_t)sat16(t32 + (int)st->out_ola[i]);  // :224-227
         t32 = (td[2 + h] * w1) >> 14;  // :229-230 (no rounding here)
@@ -932,55 +948,61 @@ __device__ __forceinline__ int api_process(const Ctx &c, const int16_t *near_noi
 // ------------------------------------------------------------------------------------------------
 // kernels
 // ------------------------------------------------------------------------------------------------
-struct __align__(16) CtaShared {
-    CtaTables tab;
-    uint32_t pad_[3];
-};
-
-__device__ __forceinline__ void load_tables(CtaTables *t) {
-    for (int k = threadIdx.x; k < 64; k += blockDim.x) {
-        const uint32_t w = kAecmTwiddle128[k];
-        t->tw[k] = make_int2(lo16(w), hi16(w));
-        t->lcg_mul[k] = kLcgJump.mul[k];
-        t->lcg_add[k] = kLcgJump.add[k];
+// ---- 1-D bulk async copies (TMA unit) between the HBM record and the warp's shared-memory copy ----
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void bulk_load_record(void *dst_smem, const void *src_gmem, uint32_t bytes, uint64_t *bar, int lane) {
+    if (lane == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(bar)));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                         smem_u32(dst_smem)),
+                     "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+                     : "memory");
     }
-    for (int k = threadIdx.x; k < 360; k += blockDim.x) t->cossin[k] = kAecmCosSinQ13[k];
-    for (int k = threadIdx.x; k < 65; k += blockDim.x) t->hann[k] = kAecmSqrtHanningQ14[k];
-    if (threadIdx.x < 32) {
-        const aecm_fft::LaneWords lw = aecm_fft::lane_words(threadIdx.x);
-        const aecm_fft::LaneBins lb = aecm_fft::lane_bins(threadIdx.x);
-        t->lane_w[threadIdx.x] = make_int4(lw.a, lw.b, lw.c, lw.d);
-        t->lane_b[threadIdx.x] = make_int4(lb.k0, lb.k1, lb.m0, lb.m1);
+    __syncwarp();
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_RECORD:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], 0;\n"
+        "@p bra DONE_RECORD;\n"
+        "bra WAIT_RECORD;\n"
+        "DONE_RECORD:\n"
+        "}\n" ::"r"(smem_u32(bar))
+        : "memory");
+}
+__device__ __forceinline__ void bulk_store_record(void *dst_gmem, const void *src_smem, uint32_t bytes, int lane) {
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> visible to the async proxy
+    __syncwarp();
+    if (lane == 0) {
+        asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst_gmem), "r"(smem_u32(src_smem)),
+                     "r"(bytes)
+                     : "memory");
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // the shared-memory source may be released
     }
 }
 
-// shared memory: [CtaShared][kWarpsPerCta x (AecmInstanceState, WarpScratch)]
-__global__ void __launch_bounds__(kWarpsPerCta * 32, 7) aecm_call_kernel(AecmBatchPlanes planes, AecmCallArgs a) {
+// shared memory: kWarpsPerCta x (AecmInstanceState, WarpScratch)
+__global__ void __launch_bounds__(kWarpsPerCta * 32, kCtasPerSm) aecm_call_kernel(AecmBatchPlanes planes, AecmCallArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    CtaShared *cs = reinterpret_cast<CtaShared *>(smem_raw);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    unsigned char *wbase = smem_raw + sizeof(CtaShared) + (size_t)warp * (sizeof(AecmInstanceState) + sizeof(WarpScratch));
+    unsigned char *wbase = smem_raw + (size_t)warp * (sizeof(AecmInstanceState) + sizeof(WarpScratch));
     AecmInstanceState *st = reinterpret_cast<AecmInstanceState *>(wbase);
     WarpScratch *sc = reinterpret_cast<WarpScratch *>(wbase + sizeof(AecmInstanceState));
 
-    load_tables(&cs->tab);
     const int row = blockIdx.x * kWarpsPerCta + warp;
-    const bool active = row < a.count;
+    if (row >= a.count) return;
     const int inst = a.first + row;
     const bool use_clean = a.near_clean != nullptr;
-    const int n_vec = (use_clean ? AECM_STATE_BYTES : AECM_STATE_BYTES_NOCLEAN) / 16;
-    uint4 *g_state = reinterpret_cast<uint4 *>(planes.state + (active ? inst : 0));
-    if (active) {
-        uint4 *s_state = reinterpret_cast<uint4 *>(st);
-        for (int k = lane; k < n_vec; k += 32) s_state[k] = g_state[k];
-    }
-    __syncthreads();
-    if (!active) return;
+    const uint32_t rec_bytes = use_clean ? AECM_STATE_BYTES : AECM_STATE_BYTES_NOCLEAN;
+    AecmInstanceState *g_state = planes.state + inst;
+    bulk_load_record(st, g_state, rec_bytes, &sc->mbar, lane);
 
     Ctx c;
     c.st = st;
     c.sc = sc;
-    c.tab = &cs->tab;
     c.far_hist = planes.far_hist + (size_t)inst * AECM_MAX_DELAY * AECM_HIST_ROW;
     c.far_ring = planes.far_ring + (size_t)inst * AECM_FAR_RING;
     c.lane = lane;
@@ -1000,11 +1022,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 7) aecm_call_kernel(AecmBat
             if (status == 0) status = r;
         }
     }
-    __syncwarp();
-    {
-        const uint4 *s_state = reinterpret_cast<const uint4 *>(st);
-        for (int k = lane; k < n_vec; k += 32) g_state[k] = s_state[k];
-    }
+    bulk_store_record(g_state, st, rec_bytes, lane);
     if (a.status && lane == 0) a.status[row] = status;
 }
 
@@ -1150,7 +1168,7 @@ int aecm_cuda_launch_init_echo_path(const AecmBatchPlanes *p, int first, int cou
 int aecm_cuda_launch_call(const AecmBatchPlanes *p, const AecmCallArgs *a, void *stream) {
     if (a->count <= 0 || a->n_calls <= 0) return 0;
     static bool attr_set = false;
-    const size_t smem = sizeof(CtaShared) + (size_t)kWarpsPerCta * (sizeof(AecmInstanceState) + sizeof(WarpScratch));
+    const size_t smem = (size_t)kWarpsPerCta * (sizeof(AecmInstanceState) + sizeof(WarpScratch));
     if (!attr_set) {
         cudaError_t e = cudaFuncSetAttribute(aecm_call_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return (int)e;
