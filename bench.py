@@ -197,47 +197,55 @@ def run_ours(args):
     total_blocks = blocks_per_inst * B * world
     value = total_blocks / (max_ms * 1e-3)
 
-    # ---- e2e: host planes through the public C ABI (H2D + kernel + D2H + sync per step) ----
+    # ---- e2e: host planes through the public C ABI, double buffered (Submit step k+1 while step k runs) ----
     e2e = None
     if not args.no_e2e:
-        Ke = min(K, 50)
-        hfar = torch.empty((B, cps * spc), dtype=torch.int16).pin_memory()
-        hnear = torch.empty_like(hfar).pin_memory()
-        hout = torch.empty_like(hfar).pin_memory()
-        hstatus = np.zeros(B, dtype=np.int32)
-        # continue the same streams: regenerate fresh audio for the e2e steps
-        efar, enear = synth_streams_torch(B, (Ke + 3) * cps * spc, fs, SEED, 40, "echo", first_inst,
-                                          sample0 + n_calls_total * spc, dev)
-        efar_h = efar.cpu().pin_memory()
-        enear_h = enear.cpu().pin_memory()
-        L = api.lib()
         import ctypes as C
 
-        def e2e_step(k):
-            a = api.StreamArgs(hfar.data_ptr(), hnear.data_ptr(), None, hout.data_ptr(), cps * spc, 0, B, spc, cps, None, 40,
-                               None, hstatus.ctypes.data)
-            # the step's inputs arrive in pinned host memory (copied here from the pre-generated host stream)
-            hfar.copy_(efar_h[:, k * cps * spc:(k + 1) * cps * spc])
-            hnear.copy_(enear_h[:, k * cps * spc:(k + 1) * cps * spc])
-            t0 = time.perf_counter()
-            r = L.AecmB200_ProcessStream(batch._h, C.byref(a))
-            t1 = time.perf_counter()
-            assert r == 0 and not hstatus.any()
-            return t1 - t0
+        Ke, Kw = min(K, 60), 4
+        # continue the same streams: fresh audio for the e2e steps, laid out [step][instance][samples] in PINNED host memory
+        efar, enear = synth_streams_torch(B, (Ke + Kw) * cps * spc, fs, SEED, 40, "echo", first_inst,
+                                          sample0 + n_calls_total * spc, dev)
+        hfar = efar.view(B, Ke + Kw, cps * spc).permute(1, 0, 2).contiguous().cpu().pin_memory()
+        hnear = enear.view(B, Ke + Kw, cps * spc).permute(1, 0, 2).contiguous().cpu().pin_memory()
+        hout = torch.empty_like(hnear).pin_memory()
+        hstatus = [np.zeros(B, dtype=np.int32) for _ in range(2)]
+        del efar, enear
+        L = api.lib()
+        plane = B * cps * spc * 2  # bytes per step and plane
 
-        for k in range(3):
-            e2e_step(k)
+        def submit(k):
+            a = api.StreamArgs(hfar.data_ptr() + k * plane, hnear.data_ptr() + k * plane, None, hout.data_ptr() + k * plane,
+                               cps * spc, 0, B, spc, cps, None, 40, None, hstatus[k % 2].ctypes.data)
+            assert L.AecmB200_SubmitStream(batch._h, C.byref(a), k % 2) == 0
+
+        def wait(k):
+            assert L.AecmB200_WaitStream(batch._h, k % 2) == 0 and not hstatus[k % 2].any()
+
+        for k in range(Kw):  # warm-up, unpipelined
+            submit(k)
+            wait(k)
         b0 = batch.read_state(0).s.tot_count
         if world > 1:
             dist.barrier()
-        secs = sum(e2e_step(3 + k) for k in range(Ke))
+        t0 = time.perf_counter()
+        submit(Kw)
+        for k in range(Kw + 1, Kw + Ke):
+            submit(k)       # H2D of step k overlaps the kernel / D2H of step k-1
+            wait(k - 1)     # results of step k-1 are in host memory
+        wait(Kw + Ke - 1)
+        secs = time.perf_counter() - t0
         tt = torch.tensor([secs], dtype=torch.float64, device=dev)
         if world > 1:
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         eb = (batch.read_state(0).s.tot_count - b0) * B * world
+        # spot-check: the e2e output of the last step equals what the device-resident path would produce is covered by
+        # the parity tests; here only make sure something was written
+        assert int(hout[Kw + Ke - 1].abs().max()) > 0
         e2e = {"value": eb / float(tt.item()), "unit": "blocks/s", "h2d_bytes_per_step": 2 * B * cps * spc * 2,
-               "d2h_bytes_per_step": B * cps * spc * 2 + B * 4, "steps": Ke,
-               "note": "AecmB200_ProcessStream on pinned host planes: H2D far+near, fused kernel, D2H out+status, stream sync"}
+               "d2h_bytes_per_step": B * cps * spc * 2 + B * 4, "steps": Ke, "ms_per_step": secs * 1e3 / Ke,
+               "note": "AecmB200_SubmitStream/WaitStream on pinned host planes, two slots: per step H2D far+near, "
+                       "fused kernel, D2H out+status, all inside the timed region"}
 
     # ---- CPU baseline beside it (rank 0, N=1 only) ----
     cpu = None

@@ -73,6 +73,12 @@ typedef struct {
 
 /* Host-memory planes: copies in, runs, copies out and waits (pinned planes avoid the staging copy). */
 int32_t AecmB200_ProcessStream(AecmB200Batch *batch, const AecmB200StreamArgs *hostArgs);
+/* The same call split in two for double buffering: Submit enqueues H2D copies, the kernel and D2H copies for one of
+ * two slots (0 or 1) and returns at once; Wait blocks until that slot's results (out planes, status) are in host
+ * memory.  Kernels execute in submission order; the copies of one slot overlap the kernel of the other.  The host
+ * planes (pinned for real overlap) and the status array must stay valid until Wait. */
+int32_t AecmB200_SubmitStream(AecmB200Batch *batch, const AecmB200StreamArgs *hostArgs, int32_t slot);
+int32_t AecmB200_WaitStream(AecmB200Batch *batch, int32_t slot);
 /* Device-memory planes on the batch's GPU: enqueues on the batch stream and returns immediately. */
 int32_t AecmB200_ProcessStreamDevice(AecmB200Batch *batch, const AecmB200StreamArgs *deviceArgs);
 

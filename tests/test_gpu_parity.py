@@ -191,3 +191,38 @@ def test_ragged_ranges_and_partial_batches():
     assert b.process_stream(far[:0], near[:0], samples_per_call=spc, first=0, count=0)[0] == 0
     assert b.process_stream(far, near, samples_per_call=spc, first=5, count=10)[0] == 12004
     b.close()
+
+
+def test_double_buffered_submit_wait_equals_synchronous():
+    """AecmB200_SubmitStream / WaitStream with two slots (copies of call k+1 overlap the kernel of call k) must give
+    exactly the outputs of the synchronous call sequence."""
+    import ctypes as C
+
+    from webrtc_aecm_b200 import AecmBatch, api
+
+    fs, spc, n, calls = 16000, 160, 256, 50
+    far, near = synth_streams(n, calls * spc, fs, seed=909, delay_ms=np.arange(n) % 90)
+    want, _, _ = ol.run_streams(far, near, fs=fs, impl="oracle")
+    # [call][instance][samples] so every call's plane is dense
+    hfar = np.ascontiguousarray(far.reshape(n, calls, spc).transpose(1, 0, 2))
+    hnear = np.ascontiguousarray(near.reshape(n, calls, spc).transpose(1, 0, 2))
+    hout = np.zeros_like(hnear)
+    status = [np.zeros(n, dtype=np.int32) for _ in range(2)]
+    b = AecmBatch(n, 0)
+    assert b.init(fs) == 0
+    L = api.lib()
+
+    def submit(k):
+        a = api.StreamArgs(hfar[k].ctypes.data, hnear[k].ctypes.data, None, hout[k].ctypes.data, spc, 0, n, spc, 1, None, 40,
+                           None, status[k % 2].ctypes.data)
+        assert L.AecmB200_SubmitStream(b._h, C.byref(a), k % 2) == 0
+
+    submit(0)
+    assert L.AecmB200_SubmitStream(b._h, None, 0) == 12003  # NULL args
+    for k in range(1, calls):
+        submit(k)
+        assert L.AecmB200_WaitStream(b._h, (k - 1) % 2) == 0 and not status[(k - 1) % 2].any()
+    assert L.AecmB200_WaitStream(b._h, (calls - 1) % 2) == 0
+    got = hout.transpose(1, 0, 2).reshape(n, calls * spc)
+    np.testing.assert_array_equal(got, want)
+    b.close()

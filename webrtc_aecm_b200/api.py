@@ -21,7 +21,8 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 
 
 def library_path() -> str:
-    return os.path.join(_HERE, "libaecm_b200.so")
+    """The in-tree build; AECM_B200_LIB overrides it (kernel-variant experiments, same ABI)."""
+    return os.environ.get("AECM_B200_LIB") or os.path.join(_HERE, "libaecm_b200.so")
 
 
 class AecmConfig(C.Structure):
@@ -88,6 +89,8 @@ def lib():
             "AecmB200_GetEchoPath": (i32, [vp, i32, vp, C.c_size_t]),
             "AecmB200_ProcessStream": (i32, [vp, C.POINTER(StreamArgs)]),
             "AecmB200_ProcessStreamDevice": (i32, [vp, C.POINTER(StreamArgs)]),
+            "AecmB200_SubmitStream": (i32, [vp, C.POINTER(StreamArgs), i32]),
+            "AecmB200_WaitStream": (i32, [vp, i32]),
             "AecmB200_BufferFarend": (i32, [vp, vp, C.c_size_t, vp]),
             "AecmB200_Process": (i32, [vp, vp, vp, vp, C.c_size_t, vp, C.c_int16, vp]),
             "AecmB200_Synchronize": (i32, [vp]), "AecmB200_CudaStream": (vp, [vp]),

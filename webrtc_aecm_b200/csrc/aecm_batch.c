@@ -12,18 +12,31 @@
 
 #include "aecm_state.h"
 
+#define AECM_SLOTS 2 /* in-flight host-plane submissions (double buffering) */
+
+/* One in-flight host-plane submission: device staging planes, a copy stream and the events that order
+ * H2D -> kernel (on the batch's compute stream, so kernels stay in submission order) -> D2H. */
+typedef struct {
+    int16_t *d_far, *d_near, *d_clean, *d_out;
+    size_t plane_samples;
+    int16_t *d_ms;
+    uint8_t *d_mask;
+    size_t mask_bytes;
+    int32_t *d_status, *h_status; /* h_status is pinned */
+    cudaStream_t copy;
+    cudaEvent_t h2d_done, kernel_done;
+    int32_t *user_status;
+    int32_t count;
+    int busy;
+} Slot;
+
 struct AecmB200Batch {
     int32_t n, device;
     AecmBatchPlanes planes;
     cudaStream_t stream;
     int owns_stream;
-    /* device staging for the host-plane calls, grown on demand */
-    int16_t *d_far, *d_near, *d_clean, *d_out;
-    size_t d_plane_samples;
-    int16_t *d_ms;
-    uint8_t *d_mask;
-    size_t d_mask_bytes;
-    int32_t *d_status;
+    Slot slot[AECM_SLOTS];  /* staging for the host-plane calls, grown on demand */
+    int32_t *d_status;      /* scratch for the control calls (set_config, echo path) */
     int16_t *d_path;
     char err[256];
 };
@@ -60,13 +73,25 @@ AecmB200Batch *AecmB200_Create(int32_t n, int32_t device) {
     if (cudaMalloc((void **)&b->planes.state, (size_t)n * sizeof(AecmInstanceState)) != cudaSuccess ||
         cudaMalloc((void **)&b->planes.far_hist, (size_t)n * AECM_MAX_DELAY * AECM_HIST_ROW * sizeof(uint16_t)) != cudaSuccess ||
         cudaMalloc((void **)&b->planes.far_ring, (size_t)n * AECM_FAR_RING * sizeof(int16_t)) != cudaSuccess ||
-        cudaMalloc((void **)&b->d_ms, (size_t)n * sizeof(int16_t)) != cudaSuccess ||
         cudaMalloc((void **)&b->d_status, (size_t)n * sizeof(int32_t)) != cudaSuccess ||
         cudaMalloc((void **)&b->d_path, AECM_BINS * sizeof(int16_t)) != cudaSuccess ||
         cudaStreamCreateWithFlags(&b->stream, cudaStreamNonBlocking) != cudaSuccess) {
         fprintf(stderr, "aecm_b200: device allocation failed: %s\n", cudaGetErrorString(cudaGetLastError()));
         AecmB200_Free(b);
         return NULL;
+    }
+    for (int i = 0; i < AECM_SLOTS; i++) {
+        Slot *sl = &b->slot[i];
+        if (cudaMalloc((void **)&sl->d_ms, (size_t)n * sizeof(int16_t)) != cudaSuccess ||
+            cudaMalloc((void **)&sl->d_status, (size_t)n * sizeof(int32_t)) != cudaSuccess ||
+            cudaMallocHost((void **)&sl->h_status, (size_t)n * sizeof(int32_t)) != cudaSuccess ||
+            cudaStreamCreateWithFlags(&sl->copy, cudaStreamNonBlocking) != cudaSuccess ||
+            cudaEventCreateWithFlags(&sl->h2d_done, cudaEventDisableTiming) != cudaSuccess ||
+            cudaEventCreateWithFlags(&sl->kernel_done, cudaEventDisableTiming) != cudaSuccess) {
+            fprintf(stderr, "aecm_b200: staging allocation failed: %s\n", cudaGetErrorString(cudaGetLastError()));
+            AecmB200_Free(b);
+            return NULL;
+        }
     }
     b->owns_stream = 1;
     /* calloc semantics of the reference's Create: an un-Init'ed instance reports AECM_UNINITIALIZED_ERROR */
@@ -85,12 +110,16 @@ void AecmB200_Free(AecmB200Batch *b) {
     cudaFree(b->planes.state);
     cudaFree(b->planes.far_hist);
     cudaFree(b->planes.far_ring);
-    cudaFree(b->d_far);
-    cudaFree(b->d_near);
-    cudaFree(b->d_clean);
-    cudaFree(b->d_out);
-    cudaFree(b->d_ms);
-    cudaFree(b->d_mask);
+    for (int i = 0; i < AECM_SLOTS; i++) {
+        Slot *sl = &b->slot[i];
+        if (sl->copy) cudaStreamSynchronize(sl->copy);
+        cudaFree(sl->d_far); cudaFree(sl->d_near); cudaFree(sl->d_clean); cudaFree(sl->d_out);
+        cudaFree(sl->d_ms); cudaFree(sl->d_mask); cudaFree(sl->d_status);
+        cudaFreeHost(sl->h_status);
+        if (sl->copy) cudaStreamDestroy(sl->copy);
+        if (sl->h2d_done) cudaEventDestroy(sl->h2d_done);
+        if (sl->kernel_done) cudaEventDestroy(sl->kernel_done);
+    }
     cudaFree(b->d_status);
     cudaFree(b->d_path);
     if (b->stream && b->owns_stream) cudaStreamDestroy(b->stream);
@@ -235,6 +264,7 @@ static void fill_call_args(AecmCallArgs *k, const AecmB200StreamArgs *a) {
     k->samples_per_call = a->nrOfSamples;
     k->n_calls = a->nCalls;
     k->ms_uniform = a->msUniform;
+    k->mask_stride = a->count;
 }
 
 int32_t AecmB200_ProcessStreamDevice(AecmB200Batch *b, const AecmB200StreamArgs *a) {
@@ -250,17 +280,17 @@ int32_t AecmB200_ProcessStreamDevice(AecmB200Batch *b, const AecmB200StreamArgs 
     return 0;
 }
 
-static int grow_planes(AecmB200Batch *b, size_t samples, int need_clean) {
-    if (samples > b->d_plane_samples) {
-        cudaFree(b->d_far); cudaFree(b->d_near); cudaFree(b->d_clean); cudaFree(b->d_out);
-        b->d_far = b->d_near = b->d_clean = b->d_out = NULL;
-        b->d_plane_samples = 0;
-        CU(b, cudaMalloc((void **)&b->d_far, samples * sizeof(int16_t)));
-        CU(b, cudaMalloc((void **)&b->d_near, samples * sizeof(int16_t)));
-        CU(b, cudaMalloc((void **)&b->d_out, samples * sizeof(int16_t)));
-        b->d_plane_samples = samples;
+static int grow_planes(AecmB200Batch *b, Slot *sl, size_t samples, int need_clean) {
+    if (samples > sl->plane_samples) {
+        cudaFree(sl->d_far); cudaFree(sl->d_near); cudaFree(sl->d_clean); cudaFree(sl->d_out);
+        sl->d_far = sl->d_near = sl->d_clean = sl->d_out = NULL;
+        sl->plane_samples = 0;
+        CU(b, cudaMalloc((void **)&sl->d_far, samples * sizeof(int16_t)));
+        CU(b, cudaMalloc((void **)&sl->d_near, samples * sizeof(int16_t)));
+        CU(b, cudaMalloc((void **)&sl->d_out, samples * sizeof(int16_t)));
+        sl->plane_samples = samples;
     }
-    if (need_clean && !b->d_clean) CU(b, cudaMalloc((void **)&b->d_clean, b->d_plane_samples * sizeof(int16_t)));
+    if (need_clean && !sl->d_clean) CU(b, cudaMalloc((void **)&sl->d_clean, sl->plane_samples * sizeof(int16_t)));
     return 0;
 }
 
@@ -271,60 +301,105 @@ static cudaError_t copy_plane(void *dst, size_t dpitch, const void *src, size_t 
     return cudaMemcpy2DAsync(dst, dpitch, src, spitch, width, rows, kind, s);
 }
 
-int32_t AecmB200_ProcessStream(AecmB200Batch *b, const AecmB200StreamArgs *h) {
-    AecmB200StreamArgs d;
+/* Host planes, asynchronous.  H2D on the slot's copy stream, the kernel on the batch's compute stream (so kernels of
+ * successive submissions run in order: every call depends on the state left by the previous one), D2H back on the
+ * copy stream.  With two slots the copies of call k+1 overlap the kernel of call k. */
+int32_t AecmB200_SubmitStream(AecmB200Batch *b, const AecmB200StreamArgs *h, int32_t slot) {
     size_t width, rows, pitch_src, pitch_dst;
+    AecmCallArgs k;
+    Slot *sl;
     int32_t rc;
     if (!b) return -1;
+    if (slot < 0 || slot >= AECM_SLOTS) return AECM_BAD_PARAMETER_ERROR;
     rc = validate_stream_args(b, h);
     if (rc) return rc;
-    if (h->count == 0) return 0;
+    sl = &b->slot[slot];
+    if (sl->busy) return AECM_BAD_PARAMETER_ERROR; /* the previous submission on this slot was not waited for */
     CU(b, cudaSetDevice(b->device));
+    sl->user_status = h->status;
+    sl->count = h->count;
+    sl->busy = 1;
+    if (h->count == 0) return 0;
     width = (size_t)h->nCalls * (size_t)h->nrOfSamples; /* samples actually used per row */
     rows = (size_t)h->count;
-    rc = grow_planes(b, rows * width, h->nearendClean != NULL);
+    rc = grow_planes(b, sl, rows * width, h->nearendClean != NULL);
     if (rc) return rc;
     pitch_src = (size_t)h->rowStride * sizeof(int16_t);
     pitch_dst = width * sizeof(int16_t);
-    d = *h;
-    d.rowStride = (int64_t)width;
-    d.farend = d.nearendNoisy = d.nearendClean = NULL;
-    d.out = NULL;
+    memset(&k, 0, sizeof(k));
     if (h->farend) {
-        CU(b, copy_plane(b->d_far, pitch_dst, h->farend, pitch_src, pitch_dst, rows, cudaMemcpyHostToDevice, b->stream));
-        d.farend = b->d_far;
+        CU(b, copy_plane(sl->d_far, pitch_dst, h->farend, pitch_src, pitch_dst, rows, cudaMemcpyHostToDevice, sl->copy));
+        k.far = sl->d_far;
     }
     if (h->nearendNoisy) {
-        CU(b, copy_plane(b->d_near, pitch_dst, h->nearendNoisy, pitch_src, pitch_dst, rows, cudaMemcpyHostToDevice, b->stream));
-        d.nearendNoisy = b->d_near;
-        d.out = b->d_out;
+        CU(b, copy_plane(sl->d_near, pitch_dst, h->nearendNoisy, pitch_src, pitch_dst, rows, cudaMemcpyHostToDevice, sl->copy));
+        k.near_noisy = sl->d_near;
+        k.out = sl->d_out;
         if (h->nearendClean) {
-            CU(b, copy_plane(b->d_clean, pitch_dst, h->nearendClean, pitch_src, pitch_dst, rows, cudaMemcpyHostToDevice, b->stream));
-            d.nearendClean = b->d_clean;
+            CU(b, copy_plane(sl->d_clean, pitch_dst, h->nearendClean, pitch_src, pitch_dst, rows, cudaMemcpyHostToDevice, sl->copy));
+            k.near_clean = sl->d_clean;
         }
     }
     if (h->msInSndCardBuf) {
-        CU(b, cudaMemcpyAsync(b->d_ms, h->msInSndCardBuf, rows * sizeof(int16_t), cudaMemcpyHostToDevice, b->stream));
-        d.msInSndCardBuf = b->d_ms;
+        CU(b, cudaMemcpyAsync(sl->d_ms, h->msInSndCardBuf, rows * sizeof(int16_t), cudaMemcpyHostToDevice, sl->copy));
+        k.ms = sl->d_ms;
     }
     if (h->farendMask) {
         const size_t mb = rows * (size_t)h->nCalls;
-        if (mb > b->d_mask_bytes) {
-            cudaFree(b->d_mask);
-            b->d_mask = NULL;
-            b->d_mask_bytes = 0;
-            CU(b, cudaMalloc((void **)&b->d_mask, mb));
-            b->d_mask_bytes = mb;
+        if (mb > sl->mask_bytes) {
+            cudaFree(sl->d_mask);
+            sl->d_mask = NULL;
+            sl->mask_bytes = 0;
+            CU(b, cudaMalloc((void **)&sl->d_mask, mb));
+            sl->mask_bytes = mb;
         }
-        CU(b, cudaMemcpyAsync(b->d_mask, h->farendMask, mb, cudaMemcpyHostToDevice, b->stream));
-        d.farendMask = b->d_mask;
+        CU(b, cudaMemcpyAsync(sl->d_mask, h->farendMask, mb, cudaMemcpyHostToDevice, sl->copy));
+        k.far_mask = sl->d_mask;
     }
-    d.status = b->d_status;
-    rc = AecmB200_ProcessStreamDevice(b, &d);
-    if (rc) return rc;
+    k.mask_stride = h->count;
+    k.status = sl->d_status;
+    k.row_stride = (int64_t)width;
+    k.first = h->first;
+    k.count = h->count;
+    k.samples_per_call = h->nrOfSamples;
+    k.n_calls = h->nCalls;
+    k.ms_uniform = h->msUniform;
+    CU(b, cudaEventRecord(sl->h2d_done, sl->copy));
+    CU(b, cudaStreamWaitEvent(b->stream, sl->h2d_done, 0));
+    CU(b, (cudaError_t)aecm_cuda_launch_call(&b->planes, &k, b->stream));
+    CU(b, cudaEventRecord(sl->kernel_done, b->stream));
+    CU(b, cudaStreamWaitEvent(sl->copy, sl->kernel_done, 0));
     if (h->nearendNoisy)
-        CU(b, copy_plane(h->out, pitch_src, b->d_out, pitch_dst, pitch_dst, rows, cudaMemcpyDeviceToHost, b->stream));
-    return copy_status_out(b, h->status, h->count);
+        CU(b, copy_plane(h->out, pitch_src, sl->d_out, pitch_dst, pitch_dst, rows, cudaMemcpyDeviceToHost, sl->copy));
+    if (h->status)
+        CU(b, cudaMemcpyAsync(sl->h_status, sl->d_status, rows * sizeof(int32_t), cudaMemcpyDeviceToHost, sl->copy));
+    return 0;
+}
+
+int32_t AecmB200_WaitStream(AecmB200Batch *b, int32_t slot) {
+    Slot *sl;
+    if (!b) return -1;
+    if (slot < 0 || slot >= AECM_SLOTS) return AECM_BAD_PARAMETER_ERROR;
+    sl = &b->slot[slot];
+    if (!sl->busy) return 0;
+    CU(b, cudaSetDevice(b->device));
+    CU(b, cudaStreamSynchronize(sl->copy));
+    if (sl->user_status && sl->count > 0) memcpy(sl->user_status, sl->h_status, (size_t)sl->count * sizeof(int32_t));
+    sl->busy = 0;
+    return 0;
+}
+
+int32_t AecmB200_ProcessStream(AecmB200Batch *b, const AecmB200StreamArgs *h) {
+    int32_t rc;
+    if (!b) return -1;
+    rc = AecmB200_WaitStream(b, 0); /* keep submission order if the caller mixes the two styles */
+    if (rc) return rc;
+    rc = AecmB200_SubmitStream(b, h, 0);
+    if (rc) {
+        b->slot[0].busy = 0;
+        return rc;
+    }
+    return AecmB200_WaitStream(b, 0);
 }
 
 int32_t AecmB200_BufferFarend(AecmB200Batch *b, const int16_t *farend, size_t n, int32_t *status) {

@@ -20,8 +20,17 @@
 namespace {
 
 constexpr unsigned kFull = 0xffffffffu;
-constexpr int kWarpsPerCta = 4;
-constexpr int kCtasPerSm = 7;  // 28 warps/SM: BASELINE configs[1] (4096 instances) is a single wave on 148 SMs
+// One 28-warp CTA per SM: the warps of an SM start together and drift less through the ~50 KB of straight-line
+// code than seven independent 4-warp CTAs do (measured: +26 % throughput), at identical residency.
+#ifndef AECM_WARPS_PER_CTA
+#define AECM_WARPS_PER_CTA 28
+#endif
+constexpr int kWarpsPerCta = AECM_WARPS_PER_CTA;
+constexpr int kCtasPerSm = 28 / kWarpsPerCta;
+#ifndef AECM_LOCKSTEP
+#define AECM_LOCKSTEP 0
+#endif
+constexpr bool kLockstep = AECM_LOCKSTEP != 0;  // CTA-wide rendezvous before every block (I-cache locality experiment)  // 28 warps/SM: BASELINE configs[1] (4096 instances) is a single wave on 148 SMs
 
 // ---- algorithm constants, aecm_defines.h:28-85 ----
 constexpr int kConvLen = 512;
@@ -792,23 +801,60 @@ __device__ __forceinline__ int fifo_move(int &rd, int &cnt, int cap, int k) {  /
 }
 
 // ------------------------------------------------------------------------------------------------
+// sample movers.  All FIFO positions and plane offsets are even in every reachable state (frames of 80, blocks
+// of 64, rewinds of 16, DelayComp stuffing of an even count), so 16-bit samples normally move as 32-bit words;
+// the 16-bit loops remain as the general fallback.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ bool word_aligned(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 3) == 0; }
+
+// CTA-wide rendezvous that keeps the warps of a CTA inside the same block of code (instruction-cache locality);
+// every warp of the CTA executes it the same number of times per call, whatever its instance is doing.
+__device__ __forceinline__ void cta_rendezvous() {
+    if (kLockstep) __syncthreads();
+}
+
+// ------------------------------------------------------------------------------------------------
 // L2: one 80-sample frame (aecm_core.cc:501-572).  The far frame comes from the HBM jitter FIFO (far_idx >= 0:
 // index of its first sample) or from the replay buffer farend_old[slot]; near/clean come from the input planes.
+// `live` is false for warps that only keep the CTA rendezvous count (no instance, error, or start-up phase).
 // ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void process_frame(const Ctx &c, int far_idx, int slot, const int16_t *near80,
+__device__ __forceinline__ void process_frame(const Ctx &c, bool live, int far_idx, int slot, const int16_t *near80,
                                               const int16_t *clean80, int16_t *out80) {
     AecmInstanceState *st = c.st;
     AecmScalars &S = st->s;
     const int lane = c.lane;
-    {   // WebRtc_WriteBuffer x2/x3, :520-524 (a full FIFO drops the excess, ring_buffer.c:150-152)
+    if (live) {  // WebRtc_WriteBuffer x2/x3, :520-524 (a full FIFO drops the excess, ring_buffer.c:150-152)
         const int n = min(AECM_FRAME_LEN, AECM_FRM_RING - S.frm_in_cnt);
         const int wr = wrap_add(S.frm_in_rd, S.frm_in_cnt, AECM_FRM_RING);
-        for (int k = lane; k < n; k += 32) {
-            const int16_t f = far_idx >= 0 ? c.far_ring[wrap_add(far_idx, k, AECM_FAR_RING)] : st->farend_old[slot][k];
-            if (far_idx >= 0) st->farend_old[slot][k] = f;  // echo_control_mobile.cc:374
-            const int w = wrap_add(wr, k, AECM_FRM_RING);
-            st->frm_far[w] = f;
-            st->frm_near[w] = near80[k];
+        if (n == AECM_FRAME_LEN && ((wr | far_idx) & 1) == 0 && word_aligned(near80)) {
+            const uint32_t *nw = reinterpret_cast<const uint32_t *>(near80);
+            const uint32_t *ring = reinterpret_cast<const uint32_t *>(c.far_ring);
+            uint32_t *old = reinterpret_cast<uint32_t *>(st->farend_old[slot]);
+            uint32_t *ff = reinterpret_cast<uint32_t *>(st->frm_far), *fn = reinterpret_cast<uint32_t *>(st->frm_near);
+#pragma unroll
+            for (int h = 0; h < 2; h++) {
+                const int k = lane + 32 * h;
+                if (k < AECM_FRAME_LEN / 2) {
+                    uint32_t f;
+                    if (far_idx >= 0) {
+                        f = ring[wrap_add(far_idx >> 1, k, AECM_FAR_RING / 2)];
+                        old[k] = f;  // echo_control_mobile.cc:374
+                    } else {
+                        f = old[k];
+                    }
+                    const int w = wrap_add(wr >> 1, k, AECM_FRM_RING / 2);
+                    ff[w] = f;
+                    fn[w] = nw[k];
+                }
+            }
+        } else {
+            for (int k = lane; k < n; k += 32) {
+                const int16_t f = far_idx >= 0 ? c.far_ring[wrap_add(far_idx, k, AECM_FAR_RING)] : st->farend_old[slot][k];
+                if (far_idx >= 0) st->farend_old[slot][k] = f;
+                const int w = wrap_add(wr, k, AECM_FRM_RING);
+                st->frm_far[w] = f;
+                st->frm_near[w] = near80[k];
+            }
         }
         S.frm_in_cnt += n;
         if (clean80) {
@@ -817,25 +863,41 @@ __device__ __forceinline__ void process_frame(const Ctx &c, int far_idx, int slo
             for (int k = lane; k < nc; k += 32) st->frm_clean[wrap_add(wc, k, AECM_FRM_RING)] = clean80[k];
             S.frm_clean_cnt += nc;
         }
-    }
-    __syncwarp();
-    while (S.frm_in_cnt >= AECM_PART_LEN) {  // :527-555
-        const int in_rd = S.frm_in_rd;
-        const int clean_rd = S.frm_clean_rd;
-        const int n = min(AECM_PART_LEN, AECM_FRM_RING - S.frm_out_cnt);
-        const int wr = wrap_add(S.frm_out_rd, S.frm_out_cnt, AECM_FRM_RING);
-        process_block(c, in_rd, clean_rd, clean80 != nullptr, wr, n);
-        fifo_move(S.frm_in_rd, S.frm_in_cnt, AECM_FRM_RING, AECM_PART_LEN);
-        if (clean80) fifo_move(S.frm_clean_rd, S.frm_clean_cnt, AECM_FRM_RING, AECM_PART_LEN);
-        S.frm_out_cnt += n;
         __syncwarp();
     }
+    // :527-555 "while (available >= PART_LEN)": a FIFO below 64 gains 80 samples, so at most two blocks per frame
+#pragma unroll 1
+    for (int blk = 0; blk < 2; blk++) {
+        cta_rendezvous();
+        if (live && S.frm_in_cnt >= AECM_PART_LEN) {
+            const int in_rd = S.frm_in_rd;
+            const int clean_rd = S.frm_clean_rd;
+            const int n = min(AECM_PART_LEN, AECM_FRM_RING - S.frm_out_cnt);
+            const int wr = wrap_add(S.frm_out_rd, S.frm_out_cnt, AECM_FRM_RING);
+            process_block(c, in_rd, clean_rd, clean80 != nullptr, wr, n);
+            fifo_move(S.frm_in_rd, S.frm_in_cnt, AECM_FRM_RING, AECM_PART_LEN);
+            if (clean80) fifo_move(S.frm_clean_rd, S.frm_clean_cnt, AECM_FRM_RING, AECM_PART_LEN);
+            S.frm_out_cnt += n;
+            __syncwarp();
+        }
+    }
+    if (!live) return;
     if (S.frm_out_cnt < AECM_FRAME_LEN)  // :559-562: rewind, re-emitting already delivered samples
         fifo_move(S.frm_out_rd, S.frm_out_cnt, AECM_FRM_RING, S.frm_out_cnt - AECM_FRAME_LEN);
     {
         const int n = min(AECM_FRAME_LEN, S.frm_out_cnt);
         const int rd = S.frm_out_rd;
-        for (int k = lane; k < n; k += 32) out80[k] = st->frm_out[wrap_add(rd, k, AECM_FRM_RING)];
+        if (n == AECM_FRAME_LEN && (rd & 1) == 0 && word_aligned(out80)) {
+            uint32_t *ow = reinterpret_cast<uint32_t *>(out80);
+            const uint32_t *fo = reinterpret_cast<const uint32_t *>(st->frm_out);
+#pragma unroll
+            for (int h = 0; h < 2; h++) {
+                const int k = lane + 32 * h;
+                if (k < AECM_FRAME_LEN / 2) ow[k] = fo[wrap_add(rd >> 1, k, AECM_FRM_RING / 2)];
+            }
+        } else {
+            for (int k = lane; k < n; k += 32) out80[k] = st->frm_out[wrap_add(rd, k, AECM_FRM_RING)];
+        }
         fifo_move(S.frm_out_rd, S.frm_out_cnt, AECM_FRM_RING, n);
     }
     __syncwarp();
@@ -860,7 +922,13 @@ __device__ __forceinline__ int api_buffer_farend(const Ctx &c, const int16_t *fa
     const int w = min(n, AECM_FAR_RING - S.far_cnt);
     int wr = S.far_rd + S.far_cnt;
     if (wr >= AECM_FAR_RING) wr -= AECM_FAR_RING;
-    for (int k = c.lane; k < w; k += 32) c.far_ring[wrap_add(wr, k, AECM_FAR_RING)] = far[k];
+    if (((wr | w) & 1) == 0 && word_aligned(far)) {
+        const uint32_t *src = reinterpret_cast<const uint32_t *>(far);
+        uint32_t *ring = reinterpret_cast<uint32_t *>(c.far_ring);
+        for (int k = c.lane; k < (w >> 1); k += 32) ring[wrap_add(wr >> 1, k, AECM_FAR_RING / 2)] = src[k];
+    } else {
+        for (int k = c.lane; k < w; k += 32) c.far_ring[wrap_add(wr, k, AECM_FAR_RING)] = far[k];
+    }
     S.far_cnt += w;
     __syncwarp();
     return 0;
@@ -887,67 +955,74 @@ __device__ __forceinline__ void est_buf_delay(AecmScalars &S) {  // echo_control
     if (S.time_for_delay_change > 25) S.wrapper_known_delay = max(S.filt_delay - 160, 0);  // never forwarded (:390-391)
 }
 
-__device__ __forceinline__ int api_process(const Ctx &c, const int16_t *near_noisy, const int16_t *near_clean,
+// `live` = the warp owns an instance and its BufferFarend/Process calls are to be executed; dead warps only keep
+// the CTA rendezvous count.
+__device__ __forceinline__ int api_process(const Ctx &c, bool live, const int16_t *near_noisy, const int16_t *near_clean,
                                            int16_t *out, int n, int ms) {
     AecmScalars &S = c.st->s;
     const int lane = c.lane;
-    int ret = 0;
-    if (S.init_flag != AECM_INIT_MAGIC) return AECM_UNINITIALIZED_ERROR;
-    if (ms < 0) { ms = 0; ret = AECM_BAD_PARAMETER_WARNING; }          // :272-278
-    else if (ms > 500) { ms = 500; ret = AECM_BAD_PARAMETER_WARNING; }
-    ms += 10;
-    S.ms_in_snd_card_buf = ms;
     const int n_frames = n / AECM_FRAME_LEN;
-    const int n_blocks10ms = n_frames / S.mult;
-
-    if (S.ec_startup) {  // :285-356
-        const int16_t *src = near_clean ? near_clean : near_noisy;
-        if (out != src)
-            for (int k = lane; k < n; k += 32) out[k] = src[k];
-        const int filled = s16(S.far_cnt) / AECM_FRAME_LEN;
-        if (S.check_buff_size) {
-            S.check_buf_size_ctr = s16(S.check_buf_size_ctr + 1);
-            if (S.counter == 0) { S.first_val = ms; S.sum = 0; }
-            const int dev = abs(S.first_val - ms);
-            const double tol = 0.2 * ms > 8 ? 0.2 * ms : 8;  // :312-313, a double comparison in the reference
-            if ((double)dev < tol) { S.sum = s16(S.sum + ms); S.counter = s16(S.counter + 1); }
-            else S.counter = 0;
-            if (S.counter * n_blocks10ms >= 6) {
-                S.buf_size_start = s16(min((3 * S.sum * S.mult) / (S.counter * 40), 50));
-                S.check_buff_size = 0;
-            }
-            if (S.check_buf_size_ctr * n_blocks10ms > 50) {
-                S.buf_size_start = s16(min((3 * ms * S.mult) / 40, 50));
-                S.check_buff_size = 0;
+    int ret = 0;
+    bool processing = false;
+    if (live) {
+        if (S.init_flag != AECM_INIT_MAGIC) {
+            ret = AECM_UNINITIALIZED_ERROR;
+        } else {
+            if (ms < 0) { ms = 0; ret = AECM_BAD_PARAMETER_WARNING; }          // :272-278
+            else if (ms > 500) { ms = 500; ret = AECM_BAD_PARAMETER_WARNING; }
+            ms += 10;
+            S.ms_in_snd_card_buf = ms;
+            const int n_blocks10ms = n_frames / S.mult;
+            if (S.ec_startup) {  // :285-356
+                const int16_t *src = near_clean ? near_clean : near_noisy;
+                if (out != src)
+                    for (int k = lane; k < n; k += 32) out[k] = src[k];
+                const int filled = s16(S.far_cnt) / AECM_FRAME_LEN;
+                if (S.check_buff_size) {
+                    S.check_buf_size_ctr = s16(S.check_buf_size_ctr + 1);
+                    if (S.counter == 0) { S.first_val = ms; S.sum = 0; }
+                    const int dev = abs(S.first_val - ms);
+                    const double tol = 0.2 * ms > 8 ? 0.2 * ms : 8;  // :312-313, a double comparison in the reference
+                    if ((double)dev < tol) { S.sum = s16(S.sum + ms); S.counter = s16(S.counter + 1); }
+                    else S.counter = 0;
+                    if (S.counter * n_blocks10ms >= 6) {
+                        S.buf_size_start = s16(min((3 * S.sum * S.mult) / (S.counter * 40), 50));
+                        S.check_buff_size = 0;
+                    }
+                    if (S.check_buf_size_ctr * n_blocks10ms > 50) {
+                        S.buf_size_start = s16(min((3 * ms * S.mult) / 40, 50));
+                        S.check_buff_size = 0;
+                    }
+                }
+                if (!S.check_buff_size) {
+                    if (filled == S.buf_size_start) {
+                        S.ec_startup = 0;
+                    } else if (filled > S.buf_size_start) {
+                        fifo_move(S.far_rd, S.far_cnt, AECM_FAR_RING, S.far_cnt - S.buf_size_start * AECM_FRAME_LEN);
+                        S.ec_startup = 0;
+                    }
+                }
+            } else {
+                processing = true;
             }
         }
-        if (!S.check_buff_size) {
-            if (filled == S.buf_size_start) {
-                S.ec_startup = 0;
-            } else if (filled > S.buf_size_start) {
-                fifo_move(S.far_rd, S.far_cnt, AECM_FAR_RING, S.far_cnt - S.buf_size_start * AECM_FRAME_LEN);
-                S.ec_startup = 0;
-            }
-        }
-    } else {  // :358-397
-        for (int i = 0; i < n_frames; i++) {
+    }
+    for (int i = 0; i < n_frames; i++) {  // :358-397
+        int far_idx = -1;
+        if (processing) {
             const int filled = s16(S.far_cnt) / AECM_FRAME_LEN;
-            int far_idx = -1;
             if (filled > 0) {  // WebRtc_ReadBuffer of 80 samples
                 far_idx = S.far_rd;
                 fifo_move(S.far_rd, S.far_cnt, AECM_FAR_RING, AECM_FRAME_LEN);
             }
             if ((i == 0 && S.fs == 8000) || (i == 1 && S.fs == 16000)) est_buf_delay(S);
-            process_frame(c, far_idx, i, near_noisy + AECM_FRAME_LEN * i,
-                          near_clean ? near_clean + AECM_FRAME_LEN * i : nullptr, out + AECM_FRAME_LEN * i);
         }
+        process_frame(c, processing, far_idx, i, near_noisy + AECM_FRAME_LEN * i,
+                      near_clean ? near_clean + AECM_FRAME_LEN * i : nullptr, out + AECM_FRAME_LEN * i);
     }
     return ret;
 }
 
-// ------------------------------------------------------------------------------------------------
-// kernels
-// ------------------------------------------------------------------------------------------------
 // ---- 1-D bulk async copies (TMA unit) between the HBM record and the warp's shared-memory copy ----
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void bulk_load_record(void *dst_smem, const void *src_gmem, uint32_t bytes, uint64_t *bar, int lane) {
@@ -993,12 +1068,13 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, kCtasPerSm) aecm_call_kerne
     WarpScratch *sc = reinterpret_cast<WarpScratch *>(wbase + sizeof(AecmInstanceState));
 
     const int row = blockIdx.x * kWarpsPerCta + warp;
-    if (row >= a.count) return;
-    const int inst = a.first + row;
+    const bool live = row < a.count;
+    if (!live && !kLockstep) return;
+    const int inst = a.first + (live ? row : 0);
     const bool use_clean = a.near_clean != nullptr;
     const uint32_t rec_bytes = use_clean ? AECM_STATE_BYTES : AECM_STATE_BYTES_NOCLEAN;
     AecmInstanceState *g_state = planes.state + inst;
-    bulk_load_record(st, g_state, rec_bytes, &sc->mbar, lane);
+    if (live) bulk_load_record(st, g_state, rec_bytes, &sc->mbar, lane);
 
     Ctx c;
     c.st = st;
@@ -1008,20 +1084,21 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, kCtasPerSm) aecm_call_kerne
     c.lane = lane;
 
     const int64_t off = (int64_t)row * a.row_stride;
-    const int ms = a.ms ? (int)a.ms[row] : a.ms_uniform;
+    const int ms = (a.ms && live) ? (int)a.ms[row] : a.ms_uniform;
     int status = 0;
     for (int call = 0; call < a.n_calls; call++) {
         const int64_t o = off + (int64_t)call * a.samples_per_call;
-        if (a.far && (!a.far_mask || a.far_mask[(size_t)call * a.count + row])) {
+        if (live && a.far && (!a.far_mask || a.far_mask[(size_t)call * a.mask_stride + row])) {
             const int r = api_buffer_farend(c, a.far + o, a.samples_per_call);
             if (status == 0) status = r;
         }
         if (a.near_noisy) {
-            const int r = api_process(c, a.near_noisy + o, use_clean ? a.near_clean + o : nullptr, a.out + o,
+            const int r = api_process(c, live, a.near_noisy + o, use_clean ? a.near_clean + o : nullptr, a.out + o,
                                       a.samples_per_call, ms);
             if (status == 0) status = r;
         }
     }
+    if (!live) return;
     bulk_store_record(g_state, st, rec_bytes, lane);
     if (a.status && lane == 0) a.status[row] = status;
 }

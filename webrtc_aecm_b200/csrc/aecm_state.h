@@ -135,13 +135,14 @@ typedef struct {
     const int16_t *near_clean; /* optional */
     int16_t *out;
     const int16_t *ms;      /* [count] per-instance msInSndCardBuf, or NULL -> ms_uniform */
-    const uint8_t *far_mask;/* optional [n_calls][count]: 0 = skip BufferFarend for that call (underrun) */
+    const uint8_t *far_mask;/* optional [n_calls][mask_stride]: 0 = skip BufferFarend for that call (underrun) */
     int32_t *status;        /* [count] first non-zero return code of the fused calls, or NULL */
     int64_t row_stride;     /* samples between consecutive instances in the planes */
     int32_t first, count;   /* instance range; plane row r belongs to instance first + r */
     int32_t samples_per_call; /* 80 or 160 */
     int32_t n_calls;        /* fused consecutive 10 ms calls */
     int32_t ms_uniform;
+    int32_t mask_stride;    /* entries between consecutive calls in far_mask (>= count) */
 } AecmCallArgs;
 
 /* all return a cudaError_t value (0 = success); launches are asynchronous on `stream` */
