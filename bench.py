@@ -37,7 +37,7 @@ SEED = 0xAEC2
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--steps", type=int, default=1000)
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=4096, help="instances per GPU (BASELINE configs[1])")
@@ -58,10 +58,12 @@ def load_peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks/throttle reasons sampled every 200 ms while the timed region runs."""
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+    """nvidia-smi clocks / throttle reasons sampled every 20 ms in the background; `window()` returns the samples
+    whose timestamps fall inside the timed region (nvidia-smi needs ~1 s to start, so it is launched early)."""
+    Q = ("timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
+    NAMES = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
 
     def __init__(self, gpu_index: int):
         self.gpu = gpu_index
@@ -70,36 +72,42 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "200", "-i", str(self.gpu)], stdout=subprocess.PIPE,
+                                          "-lms", "20", "-i", str(self.gpu)], stdout=subprocess.PIPE,
                                          stderr=subprocess.DEVNULL, text=True)
         except OSError:
             self.proc = None
 
-    def stop(self):
+    def window(self, t0: float, t1: float):
+        import datetime
+
         if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.proc.terminate()
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"], "samples": 0}
+        time.sleep(0.05)
+        self.proc.terminate()  # the exact PID we started
         try:
             out, _ = self.proc.communicate(timeout=5)
         except subprocess.TimeoutExpired:
             self.proc.kill()
             out, _ = self.proc.communicate()
-        sm, mx, reasons = [], [], set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        rows = []
         for line in out.strip().splitlines():
             f = [x.strip() for x in line.split(",")]
-            if len(f) < 9:
+            if len(f) < 8:
                 continue
             try:
-                sm.append(float(f[1]))
-                mx.append(float(f[2]))
+                ts = datetime.datetime.strptime(f[0], "%Y/%m/%d %H:%M:%S.%f").timestamp()
+                rows.append((ts, float(f[1]), float(f[2]), [n for n, v in zip(self.NAMES, f[4:8]) if v.lower().startswith("active")]))
             except ValueError:
                 continue
-            for name, v in zip(names, f[5:9]):
-                if v.lower().startswith("active"):
-                    reasons.add(name)
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+        inside = [r for r in rows if t0 - 0.02 <= r[0] <= t1 + 0.02]
+        note = "samples inside the timed region"
+        if not inside and rows:  # region shorter than the sampling period: take the nearest sample
+            inside = [min(rows, key=lambda r: abs(r[0] - 0.5 * (t0 + t1)))]
+            note = "timed region shorter than the 20 ms sampling period: nearest sample"
+        reasons = sorted({n for r in inside for n in r[3]})
+        return {"sm_mhz": float(np.median([r[1] for r in inside])) if inside else None,
+                "sm_max_mhz": max(r[2] for r in inside) if inside else None, "reasons": reasons,
+                "samples": len(inside), "note": note}
 
 
 # ---------------------------------------------------------------------------------------------------
@@ -115,16 +123,22 @@ def run_ours(args):
     local = int(os.environ.get("LOCAL_RANK", "0"))
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device (the AECM engine has no CPU path)")
+    from webrtc_aecm_b200.numa import bind_to_gpu
+
+    n_local_cpus = bind_to_gpu(local)  # host planes are first-touched on the GPU's own socket
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
+    torch.cuda.set_stream(torch.cuda.Stream(dev))  # a real (non-blocking) stream, not the legacy default stream
 
     B, fs, cps = args.batch, args.fs, args.calls_per_step
     spc = 160 if fs == 16000 else 80
     K, W = args.steps, args.warmup
     first_inst = rank * B  # weak scaling: every rank owns B instances of one global instance numbering
 
+    sampler = ClockSampler(local)
+    sampler.start()  # early: nvidia-smi takes about a second before its first sample
     batch = AecmBatch(B, local)
     stream = torch.cuda.current_stream(dev)
     batch.adopt_cuda_stream(stream.cuda_stream)  # so torch.cuda.Event brackets exactly our launches
@@ -150,15 +164,24 @@ def run_ours(args):
 
     # ---- timed streams: (W + K) steps of fresh audio, resident in HBM ----
     n_calls_total = (W + K) * cps
-    far, near = synth_streams_torch(B, n_calls_total * spc, fs, SEED, 40, "echo", first_inst, sample0, dev)
-    out = torch.empty_like(near)
     row_stride = n_calls_total * spc
+    far = torch.empty((B, row_stride), dtype=torch.int16, device=dev)
+    near = torch.empty_like(far)
+    out = torch.empty_like(far)
+    gen_calls = 100  # generate in pieces: the generator's int64 temporaries are 8x the plane size
+    for c0 in range(0, n_calls_total, gen_calls):
+        c1 = min(n_calls_total, c0 + gen_calls)
+        f, n_ = synth_streams_torch(B, (c1 - c0) * spc, fs, SEED, 40, "echo", first_inst, sample0 + c0 * spc, dev)
+        far[:, c0 * spc:c1 * spc] = f
+        near[:, c0 * spc:c1 * spc] = n_
+    del f, n_
     flush = None if args.no_flush else torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 
     def step(k):
         return batch.process_stream_device(far, near, None, out, row_stride=row_stride, samples_per_call=spc,
                                            n_calls=cps, d_status=d_status, sample_offset=k * cps * spc)
 
+    stream = torch.cuda.current_stream(dev)
     for k in range(W):
         if flush is not None:
             flush.zero_()
@@ -168,12 +191,11 @@ def run_ours(args):
     launches_before = api.lib().AecmB200_KernelLaunchCount()
     ev0 = [torch.cuda.Event(enable_timing=True) for _ in range(K)]
     ev1 = [torch.cuda.Event(enable_timing=True) for _ in range(K)]
-    sampler = ClockSampler(local)
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize(dev)
-    sampler.start()
     wall0 = time.perf_counter()
+    epoch0 = time.time()
     for k in range(K):
         if flush is not None:
             flush.zero_()  # > L2 (126 MB): every step starts with a cold L2
@@ -184,7 +206,7 @@ def run_ours(args):
         dist.barrier()
     torch.cuda.synchronize(dev)
     wall1 = time.perf_counter()
-    clocks = sampler.stop()
+    clocks = sampler.window(epoch0, time.time())
     assert rc == 0 and int(d_status.abs().max().item()) == 0
     launches = api.lib().AecmB200_KernelLaunchCount() - launches_before
     step_ms = np.array([a.elapsed_time(b) for a, b in zip(ev0, ev1)])
@@ -269,7 +291,7 @@ def run_ours(args):
                        "l2": "inputs fresh every step; L2 flushed (256 MiB memset) between steps" if flush is not None
                        else "inputs fresh every step; L2 not flushed",
                        "realtime_channels": value / (250.0 if fs == 16000 else 125.0)},
-            "clocks": clocks, "gpu_launches": int(launches),
+            "clocks": clocks, "gpu_launches": int(launches), "host": {"numa_bound_cpus": n_local_cpus},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": None, "peak_source": peak_src,
                          "algorithmic_bytes_per_block": ALGO_BYTES_PER_BLOCK, "blocks_per_launch": blocks_per_launch,

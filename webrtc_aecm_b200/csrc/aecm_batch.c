@@ -23,8 +23,9 @@ typedef struct {
     uint8_t *d_mask;
     size_t mask_bytes;
     int32_t *d_status, *h_status; /* h_status is pinned */
-    cudaStream_t copy;
+    cudaStream_t copy;      /* the slot's own stream: H2D -> kernel -> D2H all run on it */
     cudaEvent_t h2d_done, kernel_done;
+    cudaEvent_t t[5];       /* optional timing marks (AECM_B200_TRACE=1): start, after H2D, kernel start, kernel end, end */
     int32_t *user_status;
     int32_t count;
     int busy;
@@ -36,10 +37,17 @@ struct AecmB200Batch {
     cudaStream_t stream;
     int owns_stream;
     Slot slot[AECM_SLOTS];  /* staging for the host-plane calls, grown on demand */
+    cudaEvent_t last_kernel; /* kernel_done of the most recent submission (kernels must run in submission order) */
+    cudaEvent_t ev_main;
+    int main_dirty;          /* the main stream received work that later submissions must follow */
+    int slots_dirty;         /* a submission's kernel has not yet been ordered before later main-stream work */
+    int trace;
     int32_t *d_status;      /* scratch for the control calls (set_config, echo path) */
     int16_t *d_path;
     char err[256];
 };
+
+static int use_main_stream(AecmB200Batch *b);
 
 static int fail(AecmB200Batch *b, const char *what, cudaError_t e) {
     if (b) snprintf(b->err, sizeof(b->err), "%s: %s", what, cudaGetErrorString(e));
@@ -87,12 +95,20 @@ AecmB200Batch *AecmB200_Create(int32_t n, int32_t device) {
             cudaMallocHost((void **)&sl->h_status, (size_t)n * sizeof(int32_t)) != cudaSuccess ||
             cudaStreamCreateWithFlags(&sl->copy, cudaStreamNonBlocking) != cudaSuccess ||
             cudaEventCreateWithFlags(&sl->h2d_done, cudaEventDisableTiming) != cudaSuccess ||
-            cudaEventCreateWithFlags(&sl->kernel_done, cudaEventDisableTiming) != cudaSuccess) {
+            cudaEventCreateWithFlags(&sl->kernel_done, cudaEventDisableTiming) != cudaSuccess ||
+            cudaEventCreate(&sl->t[0]) != cudaSuccess || cudaEventCreate(&sl->t[1]) != cudaSuccess ||
+            cudaEventCreate(&sl->t[2]) != cudaSuccess || cudaEventCreate(&sl->t[3]) != cudaSuccess ||
+            cudaEventCreate(&sl->t[4]) != cudaSuccess) {
             fprintf(stderr, "aecm_b200: staging allocation failed: %s\n", cudaGetErrorString(cudaGetLastError()));
             AecmB200_Free(b);
             return NULL;
         }
     }
+    if (cudaEventCreateWithFlags(&b->ev_main, cudaEventDisableTiming) != cudaSuccess) {
+        AecmB200_Free(b);
+        return NULL;
+    }
+    b->trace = getenv("AECM_B200_TRACE") != NULL;
     b->owns_stream = 1;
     /* calloc semantics of the reference's Create: an un-Init'ed instance reports AECM_UNINITIALIZED_ERROR */
     if (cudaMemsetAsync(b->planes.state, 0, (size_t)n * sizeof(AecmInstanceState), b->stream) != cudaSuccess ||
@@ -119,7 +135,10 @@ void AecmB200_Free(AecmB200Batch *b) {
         if (sl->copy) cudaStreamDestroy(sl->copy);
         if (sl->h2d_done) cudaEventDestroy(sl->h2d_done);
         if (sl->kernel_done) cudaEventDestroy(sl->kernel_done);
+        for (int j = 0; j < 5; j++)
+            if (sl->t[j]) cudaEventDestroy(sl->t[j]);
     }
+    if (b->ev_main) cudaEventDestroy(b->ev_main);
     cudaFree(b->d_status);
     cudaFree(b->d_path);
     if (b->stream && b->owns_stream) cudaStreamDestroy(b->stream);
@@ -144,6 +163,7 @@ int32_t AecmB200_AdoptCudaStream(AecmB200Batch *b, void *s) {
 int32_t AecmB200_Synchronize(AecmB200Batch *b) {
     if (!b) return -1;
     CU(b, cudaSetDevice(b->device));
+    if (use_main_stream(b)) return AECM_UNSPECIFIED_ERROR;
     CU(b, cudaStreamSynchronize(b->stream));
     return 0;
 }
@@ -160,6 +180,17 @@ void AecmB200_HostFree(void *p) {
 size_t AecmB200_StateBytes(void) { return sizeof(AecmInstanceState); }
 int64_t AecmB200_KernelLaunchCount(void) { return aecm_cuda_kernel_launch_count(); }
 
+/* Called before enqueuing anything on the main stream: order it after the kernels of earlier submissions and
+ * remember that later submissions have to follow it. */
+static int use_main_stream(AecmB200Batch *b) {
+    if (b->slots_dirty && b->last_kernel) {
+        CU(b, cudaStreamWaitEvent(b->stream, b->last_kernel, 0));
+        b->slots_dirty = 0;
+    }
+    b->main_dirty = 1;
+    return 0;
+}
+
 static int range_ok(const AecmB200Batch *b, int32_t first, int32_t count) {
     return first >= 0 && count >= 0 && (int64_t)first + count <= b->n;
 }
@@ -169,6 +200,7 @@ int32_t AecmB200_ReadState(AecmB200Batch *b, int32_t instance, void *dst, size_t
     if (!dst) return AECM_NULL_POINTER_ERROR;
     if (!range_ok(b, instance, 1) || bytes > sizeof(AecmInstanceState)) return AECM_BAD_PARAMETER_ERROR;
     CU(b, cudaSetDevice(b->device));
+    if (use_main_stream(b)) return AECM_UNSPECIFIED_ERROR;
     CU(b, cudaMemcpyAsync(dst, b->planes.state + instance, bytes, cudaMemcpyDeviceToHost, b->stream));
     CU(b, cudaStreamSynchronize(b->stream));
     return 0;
@@ -178,6 +210,7 @@ int32_t AecmB200_Reset(AecmB200Batch *b, int32_t first, int32_t count) {
     if (!b) return -1;
     if (!range_ok(b, first, count)) return AECM_BAD_PARAMETER_ERROR;
     CU(b, cudaSetDevice(b->device));
+    if (use_main_stream(b)) return AECM_UNSPECIFIED_ERROR;
     CU(b, cudaMemsetAsync(b->planes.state + first, 0, (size_t)count * sizeof(AecmInstanceState), b->stream));
     CU(b, cudaStreamSynchronize(b->stream));
     return 0;
@@ -188,6 +221,7 @@ int32_t AecmB200_Init(AecmB200Batch *b, int32_t first, int32_t count, int32_t fs
     if (fs != 8000 && fs != 16000) return AECM_BAD_PARAMETER_ERROR; /* echo_control_mobile.cc:150-152 */
     if (!range_ok(b, first, count)) return AECM_BAD_PARAMETER_ERROR;
     CU(b, cudaSetDevice(b->device));
+    if (use_main_stream(b)) return AECM_UNSPECIFIED_ERROR;
     CU(b, (cudaError_t)aecm_cuda_launch_init(&b->planes, first, count, fs, b->stream));
     return 0;
 }
@@ -202,6 +236,7 @@ int32_t AecmB200_SetConfig(AecmB200Batch *b, int32_t first, int32_t count, AecmC
     if (!b) return -1;
     if (!range_ok(b, first, count)) return AECM_BAD_PARAMETER_ERROR;
     CU(b, cudaSetDevice(b->device));
+    if (use_main_stream(b)) return AECM_UNSPECIFIED_ERROR;
     CU(b, (cudaError_t)aecm_cuda_launch_set_config(&b->planes, first, count, cfg.cngMode, cfg.echoMode, b->d_status, b->stream));
     return copy_status_out(b, status, count);
 }
@@ -215,6 +250,7 @@ int32_t AecmB200_InitEchoPath(AecmB200Batch *b, int32_t instance, const void *pa
     if (size_bytes != WebRtcAecm_echo_path_size_bytes()) return AECM_BAD_PARAMETER_ERROR;
     if (!range_ok(b, instance, 1)) return AECM_BAD_PARAMETER_ERROR;
     CU(b, cudaSetDevice(b->device));
+    if (use_main_stream(b)) return AECM_UNSPECIFIED_ERROR;
     CU(b, cudaMemcpyAsync(b->d_path, path, size_bytes, cudaMemcpyHostToDevice, b->stream));
     CU(b, (cudaError_t)aecm_cuda_launch_init_echo_path(&b->planes, instance, 1, b->d_path, AECM_BINS, b->d_status, b->stream));
     rc = copy_status_out(b, &st, 1);
@@ -229,6 +265,7 @@ int32_t AecmB200_GetEchoPath(AecmB200Batch *b, int32_t instance, void *path, siz
     if (size_bytes != WebRtcAecm_echo_path_size_bytes()) return AECM_BAD_PARAMETER_ERROR;
     if (!range_ok(b, instance, 1)) return AECM_BAD_PARAMETER_ERROR;
     CU(b, cudaSetDevice(b->device));
+    if (use_main_stream(b)) return AECM_UNSPECIFIED_ERROR;
     base = (const char *)(b->planes.state + instance);
     CU(b, cudaMemcpyAsync(&flag, base + offsetof(AecmInstanceState, s) + offsetof(AecmScalars, init_flag), sizeof(flag),
                           cudaMemcpyDeviceToHost, b->stream));
@@ -275,6 +312,7 @@ int32_t AecmB200_ProcessStreamDevice(AecmB200Batch *b, const AecmB200StreamArgs 
     if (rc) return rc;
     if (a->count == 0) return 0;
     CU(b, cudaSetDevice(b->device));
+    if (use_main_stream(b)) return AECM_UNSPECIFIED_ERROR;
     fill_call_args(&k, a);
     CU(b, (cudaError_t)aecm_cuda_launch_call(&b->planes, &k, b->stream));
     return 0;
@@ -326,6 +364,14 @@ int32_t AecmB200_SubmitStream(AecmB200Batch *b, const AecmB200StreamArgs *h, int
     if (rc) return rc;
     pitch_src = (size_t)h->rowStride * sizeof(int16_t);
     pitch_dst = width * sizeof(int16_t);
+    /* earlier work on the batch's main stream (Init, set_config, device-plane calls) comes first */
+    if (b->main_dirty) {
+        int i;
+        CU(b, cudaEventRecord(b->ev_main, b->stream));
+        for (i = 0; i < AECM_SLOTS; i++) CU(b, cudaStreamWaitEvent(b->slot[i].copy, b->ev_main, 0));
+        b->main_dirty = 0;
+    }
+    if (b->trace) CU(b, cudaEventRecord(sl->t[0], sl->copy));
     memset(&k, 0, sizeof(k));
     if (h->farend) {
         CU(b, copy_plane(sl->d_far, pitch_dst, h->farend, pitch_src, pitch_dst, rows, cudaMemcpyHostToDevice, sl->copy));
@@ -364,15 +410,20 @@ int32_t AecmB200_SubmitStream(AecmB200Batch *b, const AecmB200StreamArgs *h, int
     k.samples_per_call = h->nrOfSamples;
     k.n_calls = h->nCalls;
     k.ms_uniform = h->msUniform;
-    CU(b, cudaEventRecord(sl->h2d_done, sl->copy));
-    CU(b, cudaStreamWaitEvent(b->stream, sl->h2d_done, 0));
-    CU(b, (cudaError_t)aecm_cuda_launch_call(&b->planes, &k, b->stream));
-    CU(b, cudaEventRecord(sl->kernel_done, b->stream));
-    CU(b, cudaStreamWaitEvent(sl->copy, sl->kernel_done, 0));
+    if (b->trace) CU(b, cudaEventRecord(sl->t[1], sl->copy));
+    /* the state recurrence: this kernel must follow the previous submission's kernel (on the other slot's stream) */
+    if (b->last_kernel) CU(b, cudaStreamWaitEvent(sl->copy, b->last_kernel, 0));
+    if (b->trace) CU(b, cudaEventRecord(sl->t[2], sl->copy));
+    CU(b, (cudaError_t)aecm_cuda_launch_call(&b->planes, &k, sl->copy));
+    CU(b, cudaEventRecord(sl->kernel_done, sl->copy));
+    if (b->trace) CU(b, cudaEventRecord(sl->t[3], sl->copy));
+    b->last_kernel = sl->kernel_done;
+    b->slots_dirty = 1; /* later main-stream work must see this call's state: see use_main_stream() */
     if (h->nearendNoisy)
         CU(b, copy_plane(h->out, pitch_src, sl->d_out, pitch_dst, pitch_dst, rows, cudaMemcpyDeviceToHost, sl->copy));
     if (h->status)
         CU(b, cudaMemcpyAsync(sl->h_status, sl->d_status, rows * sizeof(int32_t), cudaMemcpyDeviceToHost, sl->copy));
+    if (b->trace) CU(b, cudaEventRecord(sl->t[4], sl->copy));
     return 0;
 }
 
@@ -384,6 +435,15 @@ int32_t AecmB200_WaitStream(AecmB200Batch *b, int32_t slot) {
     if (!sl->busy) return 0;
     CU(b, cudaSetDevice(b->device));
     CU(b, cudaStreamSynchronize(sl->copy));
+    if (b->trace && sl->count > 0) {
+        float h2d = 0, gap = 0, ker = 0, d2h = 0;
+        cudaEventElapsedTime(&h2d, sl->t[0], sl->t[1]);
+        cudaEventElapsedTime(&gap, sl->t[1], sl->t[2]);
+        cudaEventElapsedTime(&ker, sl->t[2], sl->t[3]);
+        cudaEventElapsedTime(&d2h, sl->t[3], sl->t[4]);
+        fprintf(stderr, "aecm_b200 trace slot %d: h2d %.1f us, wait-for-previous-kernel %.1f us, kernel %.1f us, d2h %.1f us\n",
+                slot, h2d * 1e3f, gap * 1e3f, ker * 1e3f, d2h * 1e3f);
+    }
     if (sl->user_status && sl->count > 0) memcpy(sl->user_status, sl->h_status, (size_t)sl->count * sizeof(int32_t));
     sl->busy = 0;
     return 0;
