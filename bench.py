@@ -112,7 +112,12 @@ class ClockSampler:
 
 # ---------------------------------------------------------------------------------------------------
 def run_ours(args):
+    # torch's intra-op OpenMP pool spin-waits on every core after each CPU op and starves the thread that
+    # drives the GPU (measured: 3x slower host-plane steps); torchrun sets this for its workers, do the same here
+    os.environ.setdefault("OMP_NUM_THREADS", "1")
     import torch
+
+    torch.set_num_threads(1)
     import torch.distributed as dist
 
     from webrtc_aecm_b200 import AecmBatch, api

@@ -7,7 +7,9 @@ import sys
 import time
 
 import numpy as np
+os.environ.setdefault('OMP_NUM_THREADS', '1')
 import torch
+torch.set_num_threads(1)
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from webrtc_aecm_b200 import AecmBatch, api  # noqa: E402
