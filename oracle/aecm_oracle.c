@@ -71,11 +71,18 @@ static int16_t neg16(int16_t v) { return (int16_t)(-(int32_t)v); } /* -(-32768) 
 /* WEBRTC_SPL_ABS_W16 stored into an int16_t (aecm_core_c.cc:350-351): |-32768| stays -32768 */
 static int16_t abs16_wrap(int16_t v) { return v >= 0 ? v : neg16(v); }
 
-/* WEBRTC_SPL_SHIFT_W32 on signed / unsigned operands, signal_processing_library.h:130 */
+/* WEBRTC_SPL_SHIFT_W32 on signed / unsigned operands, signal_processing_library.h:130.  One call site
+ * (aecm_core.cc:911, the NLMS rescaling) reaches shift counts of 32 and more on loud-far / near-silent input --
+ * undefined in C; the reference library as compiled for x86 executes SAR/SHL, which use the count modulo 32
+ * (verified with a UBSan build of the reference: reports at aecm_core.cc:911, and this restatement stays
+ * bit-identical to both the -O1 UBSan and the -O3 builds).  Counts are therefore masked explicitly. */
+static unsigned g_wide_shift_events; /* how often a count outside [-31, 31] was seen (test hook) */
+unsigned oracle_debug_wide_shift_events(void) { return g_wide_shift_events; }
 static int32_t shift_s32(int32_t x, int c) {
-    return c >= 0 ? (int32_t)((uint32_t)x * ((uint32_t)1 << c)) : x >> -c;
+    if (c > 31 || c < -31) g_wide_shift_events++;
+    return c >= 0 ? (int32_t)((uint32_t)x << (c & 31)) : x >> ((-c) & 31);
 }
-static uint32_t shift_u32(uint32_t x, int c) { return c >= 0 ? x * ((uint32_t)1 << c) : x >> -c; }
+static uint32_t shift_u32(uint32_t x, int c) { return c >= 0 ? x << (c & 31) : x >> ((-c) & 31); }
 
 static int32_t div_w32_w16(int32_t num, int16_t den) { /* signal_processing_library.cc:116-123 */
     return den != 0 ? num / den : (int32_t)0x7FFFFFFF;

@@ -137,6 +137,7 @@ void oracle_rand_u_array(int16_t *v, int n, uint32_t *seed); /* signal_processin
 int oracle_norm_w16(int16_t a);                   /* spl_inl.h:107-111 */
 int oracle_norm_w32(int32_t a);                   /* spl_inl.h:96-98 */
 int oracle_norm_u32(uint32_t a);                  /* spl_inl.h:101-103 */
+unsigned oracle_debug_wide_shift_events(void);    /* times aecm_core.cc:911 saw a shift count beyond +-31 (not thread safe) */
 /* one block of the core, aecm_core_c.cc:368-711; instance must be initialised */
 int oracle_process_block(OracleAecm *a, const int16_t *far64, const int16_t *near64,
                          const int16_t *clean64, int16_t *out64);

@@ -45,6 +45,12 @@ CASES = [
     _c("16k_far_only", special="far_only", kind="stress", seconds=3.0, seed=200),
     _c("16k_full_scale_alternating", special="fullscale", seconds=2.0),
     _c("8k_full_scale_alternating", fs=8000, special="fullscale", seconds=2.0),
+    # adversarial families that drive the NLMS rescaling shift (aecm_core.cc:906-912) beyond 31 bits -- undefined
+    # in C, x86 SAR semantics in the reference as built (found with a UBSan build of the reference)
+    _c("16k_adv_gated_tone_dc_near", special="adv_gated", seconds=12.0, seed=316),
+    _c("8k_adv_gated_tone_dc_near_mode0", fs=8000, special="adv_gated", seconds=12.0, seed=300, echo_mode=0, cng=0),
+    _c("8k_adv_tone_far_whisper_near", fs=8000, special="adv_whisper", seconds=12.0, seed=303, echo_mode=0, cng=0),
+    _c("16k_adv_loud_far_zero_near_mode4", special="adv_zero_near", seconds=12.0, seed=304, echo_mode=4, ms=[0, 120, 500, 40]),
 ]
 CASE_BY_NAME = {c["name"]: c for c in CASES}
 
@@ -70,6 +76,20 @@ def make_inputs(case):
         far[:] = 32767
         far[:, ::2] = -32768
         near = far.copy()
+    elif case["special"] and case["special"].startswith("adv_"):
+        rng = np.random.default_rng(case["seed"])
+        t = np.arange(total)
+        f0 = rng.integers(100, fs // 2 - 100, size=(n, 1))
+        tone = (30000 * np.sin(2 * np.pi * f0 * t[None, :] / fs)).astype(np.int16)
+        if case["special"] == "adv_gated":      # loud far tone gated at 8 Hz, near = constant 1 LSB
+            far = (tone * ((t // (fs // 8)) % 2).astype(np.int16)).astype(np.int16)
+            near = np.full((n, total), 1, np.int16)
+        elif case["special"] == "adv_whisper":  # loud far tone, near = sparse +-1 LSB clicks
+            far = tone
+            near = ((rng.random((n, total)) < 0.02) * rng.choice([-1, 1], size=(n, total))).astype(np.int16)
+        else:                                   # full-scale far noise, near digital zero
+            far = rng.integers(-32768, 32767, size=(n, total)).astype(np.int16)
+            near = np.zeros((n, total), np.int16)
     clean = None
     if case["clean"]:
         clean = synth_streams(n, total, fs, seed=case["seed"] + 1000, delay_ms=10, kind="echo")[1]

@@ -122,3 +122,21 @@ def test_startup_gate_and_output_lag():
     err = {lag: np.abs(out[0, seg].astype(int) - near[0, seg.start - lag:seg.stop - lag].astype(int)).mean()
            for lag in (0, 64, 96, 112, 128)}
     assert min(err, key=err.get) == 112 and err[112] < 0.05 * err[0]
+
+
+def test_adversarial_cases_reach_the_wide_shift_corner():
+    """The adv_* cases exist to exercise aecm_core.cc:906-912 with |shift2ResChan| > 31 (undefined in C, x86 SAR
+    semantics in the reference as built); make sure they really do."""
+    from cases import CASE_BY_NAME
+
+    lib = ol.oracle()
+    lib.oracle_debug_wide_shift_events.restype = C.c_uint
+    hit = 0
+    for name in ("16k_adv_gated_tone_dc_near", "8k_adv_gated_tone_dc_near_mode0"):
+        before = lib.oracle_debug_wide_shift_events()
+        case = CASE_BY_NAME[name]
+        far, near, clean, ms = make_inputs(case)
+        ol.run_streams(far, near, fs=case["fs"], samples_per_call=case["spc"], impl="oracle", ms=ms, cng_mode=case["cng"],
+                       echo_mode=case["echo_mode"], threads=1)
+        hit += lib.oracle_debug_wide_shift_events() - before
+    assert hit >= 10
