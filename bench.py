@@ -55,6 +55,15 @@ def prep_calls(spc):
     return (calls + 39) // 40 * 40
 
 
+def load_traffic(batch, fs, cps):
+    """Measured DRAM bytes per launch of the hot kernel for this workload (ncu capture), or None."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            return json.load(f)[f"batch{batch}_fs{fs}_cps{cps}"]["bytes_per_launch"]
+    except (OSError, KeyError, ValueError):
+        return None
+
+
 def load_peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -309,7 +318,8 @@ def run_ours(args):
                        "realtime_channels": value / (250.0 if fs == 16000 else 125.0)},
             "clocks": clocks, "gpu_launches": int(launches), "host": {"numa_bound_cpus": n_local_cpus},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "peak_source": peak_src,
+                         "traffic": load_traffic(B, fs, cps), "traffic_unit": "bytes per launch (ncu dram read+write)",
+                         "algorithmic_bytes_per_launch": blocks_per_launch * ALGO_BYTES_PER_BLOCK, "peak_source": peak_src,
                          "algorithmic_bytes_per_block": ALGO_BYTES_PER_BLOCK, "blocks_per_launch": blocks_per_launch,
                          "kernel_ms": kernel_s * 1e3,
                          "note": "integer-issue bound kernel; see DESIGN.md for the issue-slot roofline"},

@@ -207,13 +207,10 @@ __device__ __forceinline__ void time_to_frequency(const Ctx &c, const int16_t *c
             const int i = p < 2 ? lane + 32 * p : 64;
             const int re = bre[n][p];
             const int im = (i == 0 || i == 64) ? 0 : s16(-bim[n][p]);  // :188-190, :296-297
-            int mag;
-            if (re == 0) mag = abs(im);       // :305-308; |-32768| = 32768 as uint16
-            else if (im == 0) mag = abs(re);
-            else {
-                const uint32_t e = (uint32_t)(re * re) + (uint32_t)(im * im);  // :350-354 with AddSatW32
-                mag = sqrt_floor((int)min(e, 0x7fffffffu));
-            }
+            // :305-358.  The reference short-cuts re == 0 / im == 0 to |im| / |re| (as uint16, so |-32768| = 32768);
+            // floor(sqrt(v*v)) = |v| exactly, so the general formula (with the AddSatW32 clamp) covers all three cases.
+            const uint32_t e = (uint32_t)(re * re) + (uint32_t)(im * im);
+            const int mag = sqrt_floor((int)min(e, 0x7fffffffu));
             if (p < 2 || lane == 0) {
                 mag_out[n][i] = (uint16_t)mag;
                 if (cplx_out[n]) cplx_out[n][i] = pack16(re, im);
