@@ -87,6 +87,19 @@ int32_t AecmB200_BufferFarend(AecmB200Batch *batch, const int16_t *farend, size_
 int32_t AecmB200_Process(AecmB200Batch *batch, const int16_t *nearendNoisy, const int16_t *nearendClean, int16_t *out,
                          size_t nrOfSamples, const int16_t *msInSndCardBuf, int16_t msUniform, int32_t *status);
 
+/* Multi-GPU group: nInstances split into contiguous shards (ceil-split), one batch per entry of devices[] (NULL =
+ * devices 0..nDevices-1), driven from the calling thread.  Instances are independent, so shards never exchange
+ * data: a group call submits every shard's slice of the host planes asynchronously, then waits for all of them.
+ * first/count in the args address the group's global instance numbering; farendMask is not supported here. */
+typedef struct AecmB200Group AecmB200Group;
+AecmB200Group *AecmB200_GroupCreate(int32_t nInstances, int32_t nDevices, const int32_t *devices);
+void AecmB200_GroupFree(AecmB200Group *group);
+int32_t AecmB200_GroupNumShards(const AecmB200Group *group);
+AecmB200Batch *AecmB200_GroupShard(const AecmB200Group *group, int32_t shard, int32_t *first, int32_t *count);
+int32_t AecmB200_GroupInit(AecmB200Group *group, int32_t sampFreq);
+int32_t AecmB200_GroupSetConfig(AecmB200Group *group, AecmConfig config, int32_t *status);
+int32_t AecmB200_GroupProcessStream(AecmB200Group *group, const AecmB200StreamArgs *hostArgs);
+
 /* stream plumbing: the batch owns a CUDA stream unless one is adopted (e.g. the caller's current stream) */
 int32_t AecmB200_Synchronize(AecmB200Batch *batch);
 void *AecmB200_CudaStream(const AecmB200Batch *batch);

@@ -226,3 +226,44 @@ def test_double_buffered_submit_wait_equals_synchronous():
     got = hout.transpose(1, 0, 2).reshape(n, calls * spc)
     np.testing.assert_array_equal(got, want)
     b.close()
+
+
+def test_group_sharding_over_devices_matches_oracle():
+    """AecmB200_Group*: the instance range is ceil-split into shards (here: three shards, all placed on GPU 0 unless
+    more GPUs are visible) and every shard processes its slice of the host planes; ragged sub-ranges included."""
+    import ctypes as C
+
+    from webrtc_aecm_b200 import api
+
+    L = api.lib()
+    ndev = max(1, L.AecmB200_DeviceCount())
+    fs, spc, n, calls, shards = 16000, 160, 11, 40, 3
+    far, near = synth_streams(n, calls * spc, fs, seed=1212, delay_ms=40)
+    want, _, _ = ol.run_streams(far, near, fs=fs, impl="oracle")
+    devs = (C.c_int32 * shards)(*[i % ndev for i in range(shards)])
+    g = L.AecmB200_GroupCreate(n, shards, devs)
+    assert g and L.AecmB200_GroupNumShards(g) == shards
+    f0, c0 = C.c_int32(), C.c_int32()
+    sizes = []
+    for i in range(shards):
+        assert L.AecmB200_GroupShard(g, i, C.byref(f0), C.byref(c0))
+        sizes.append((f0.value, c0.value))
+    assert sizes == [(0, 4), (4, 4), (8, 3)]
+    assert L.AecmB200_GroupInit(g, fs) == 0
+    st = np.zeros(n, dtype=np.int32)
+    assert L.AecmB200_GroupSetConfig(g, api.AecmConfig(1, 3), st.ctypes.data) == 0 and not st.any()
+    out = np.zeros_like(near)
+    half = calls // 2 * spc
+    for sl in (slice(0, half), slice(half, calls * spc)):  # two group calls, fused 20 x 10 ms each
+        f, nr = np.ascontiguousarray(far[:, sl]), np.ascontiguousarray(near[:, sl])
+        o = np.zeros_like(nr)
+        a = api.StreamArgs(f.ctypes.data, nr.ctypes.data, None, o.ctypes.data, f.shape[1], 0, n, spc, f.shape[1] // spc, None,
+                           40, None, st.ctypes.data)
+        assert L.AecmB200_GroupProcessStream(g, C.byref(a)) == 0 and not st.any()
+        out[:, sl] = o
+    np.testing.assert_array_equal(out, want)
+    # a ragged sub-range that straddles two shards: instances 2..9 only
+    a = api.StreamArgs(f.ctypes.data, nr.ctypes.data, None, o.ctypes.data, f.shape[1], 2, 8, spc, 1, None, 40, None, None)
+    assert L.AecmB200_GroupProcessStream(g, C.byref(a)) == 0
+    assert L.AecmB200_GroupProcessStream(g, None) == 12003
+    L.AecmB200_GroupFree(g)

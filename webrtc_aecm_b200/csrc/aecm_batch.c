@@ -496,3 +496,111 @@ int32_t AecmB200_Process(AecmB200Batch *b, const int16_t *near_noisy, const int1
     a.status = status;
     return AecmB200_ProcessStream(b, &a);
 }
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Multi-GPU group: N instances split into contiguous shards, one batch per device, driven from one host thread.
+ * Instances share nothing, so there is no exchange between shards: a group call submits the
+ * shard-local part of the planes to every device (asynchronously) and then waits for all of them.
+ * ------------------------------------------------------------------------------------------------------------ */
+struct AecmB200Group {
+    int32_t n, n_shards;
+    AecmB200Batch **shard;
+    int32_t *first; /* n_shards + 1 offsets */
+};
+
+AecmB200Group *AecmB200_GroupCreate(int32_t n, int32_t n_devices, const int32_t *devices) {
+    AecmB200Group *g;
+    int i;
+    if (n <= 0 || n_devices <= 0 || n_devices > n) return NULL;
+    g = (AecmB200Group *)calloc(1, sizeof(*g));
+    if (!g) return NULL;
+    g->n = n;
+    g->n_shards = n_devices;
+    g->shard = (AecmB200Batch **)calloc((size_t)n_devices, sizeof(*g->shard));
+    g->first = (int32_t *)calloc((size_t)n_devices + 1, sizeof(int32_t));
+    if (!g->shard || !g->first) {
+        AecmB200_GroupFree(g);
+        return NULL;
+    }
+    for (i = 0; i < n_devices; i++) { /* ceil-split: the first n % n_devices shards get one more instance */
+        const int32_t base = n / n_devices, extra = n % n_devices;
+        g->first[i + 1] = g->first[i] + base + (i < extra ? 1 : 0);
+        g->shard[i] = AecmB200_Create(g->first[i + 1] - g->first[i], devices ? devices[i] : i);
+        if (!g->shard[i]) {
+            AecmB200_GroupFree(g);
+            return NULL;
+        }
+    }
+    return g;
+}
+
+void AecmB200_GroupFree(AecmB200Group *g) {
+    int i;
+    if (!g) return;
+    for (i = 0; g->shard && i < g->n_shards; i++) AecmB200_Free(g->shard[i]);
+    free(g->shard);
+    free(g->first);
+    free(g);
+}
+
+int32_t AecmB200_GroupNumShards(const AecmB200Group *g) { return g ? g->n_shards : -1; }
+
+AecmB200Batch *AecmB200_GroupShard(const AecmB200Group *g, int32_t i, int32_t *first, int32_t *count) {
+    if (!g || i < 0 || i >= g->n_shards) return NULL;
+    if (first) *first = g->first[i];
+    if (count) *count = g->first[i + 1] - g->first[i];
+    return g->shard[i];
+}
+
+int32_t AecmB200_GroupInit(AecmB200Group *g, int32_t fs) {
+    int i;
+    int32_t rc;
+    if (!g) return -1;
+    for (i = 0; i < g->n_shards; i++) {
+        rc = AecmB200_Init(g->shard[i], 0, g->first[i + 1] - g->first[i], fs);
+        if (rc) return rc;
+    }
+    return 0;
+}
+
+int32_t AecmB200_GroupSetConfig(AecmB200Group *g, AecmConfig cfg, int32_t *status) {
+    int i;
+    int32_t rc;
+    if (!g) return -1;
+    for (i = 0; i < g->n_shards; i++) {
+        rc = AecmB200_SetConfig(g->shard[i], 0, g->first[i + 1] - g->first[i], cfg, status ? status + g->first[i] : NULL);
+        if (rc) return rc;
+    }
+    return 0;
+}
+
+int32_t AecmB200_GroupProcessStream(AecmB200Group *g, const AecmB200StreamArgs *h) {
+    int i;
+    int32_t rc = 0, worst = 0;
+    if (!g) return -1;
+    if (!h) return AECM_NULL_POINTER_ERROR;
+    if (h->first < 0 || h->count < 0 || (int64_t)h->first + h->count > g->n) return AECM_BAD_PARAMETER_ERROR;
+    if (h->farendMask) return AECM_UNSUPPORTED_FUNCTION_ERROR; /* the mask is laid out per call over the whole range */
+    for (i = 0; i < g->n_shards; i++) { /* submit the shard-local slice of the range to every device ... */
+        const int32_t lo = h->first > g->first[i] ? h->first : g->first[i];
+        const int32_t hi = h->first + h->count < g->first[i + 1] ? h->first + h->count : g->first[i + 1];
+        AecmB200StreamArgs a = *h;
+        const int64_t row = (int64_t)lo - h->first; /* row of the caller's planes where this slice starts */
+        if (hi <= lo) continue;
+        a.first = lo - g->first[i];
+        a.count = hi - lo;
+        if (h->farend) a.farend = h->farend + row * h->rowStride;
+        if (h->nearendNoisy) a.nearendNoisy = h->nearendNoisy + row * h->rowStride;
+        if (h->nearendClean) a.nearendClean = h->nearendClean + row * h->rowStride;
+        if (h->out) a.out = h->out + row * h->rowStride;
+        if (h->msInSndCardBuf) a.msInSndCardBuf = h->msInSndCardBuf + row;
+        if (h->status) a.status = h->status + row;
+        rc = AecmB200_SubmitStream(g->shard[i], &a, 0);
+        if (rc) worst = rc;
+    }
+    for (i = 0; i < g->n_shards; i++) { /* ... then collect */
+        rc = AecmB200_WaitStream(g->shard[i], 0);
+        if (rc) worst = rc;
+    }
+    return worst;
+}
