@@ -8,8 +8,9 @@
 //
 // Lane mapping: 65 frequency bins -> bins lane, lane+32 and (lane 0 only) bin 64; 128 time samples ->
 // 4 per lane; the 32 delay-estimator bands -> one per lane (so __ballot_sync *is* the binary spectrum);
-// 100 delay candidates -> 4 strided passes.  Scalar state-machine code runs redundantly on all lanes on
-// the shared-memory copy (every lane writes the same value), which avoids broadcasts.
+// 100 delay candidates -> 4 strided passes.  Warp-uniform state-machine code is computed redundantly by all lanes in
+// registers (no broadcasts); the scalars themselves are read from the shared-memory record and written back by lane 0
+// only, with __syncwarp() between the last read and the write and after it (compute-sanitizer racecheck: 0 hazards).
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -225,8 +226,7 @@ __device__ __forceinline__ void time_to_frequency(const Ctx &c, const int16_t *c
 // ------------------------------------------------------------------------------------------------
 // binary spectrum of bands 12..43 (delay_estimator_wrapper.cc:92-125): lane l <-> band 12+l <-> bit l
 // ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t binary_spectrum(const uint16_t *spec, int32_t *thr, int q, int32_t &initialized,
-                                                    int lane) {
+__device__ __forceinline__ uint32_t binary_spectrum(const uint16_t *spec, int32_t *thr, int q, int &initialized, int lane) {
     const int sp = spec[12 + lane];
     const int s15 = (int)((uint32_t)sp << (15 - q));
     int t = thr[lane];
@@ -240,10 +240,11 @@ __device__ __forceinline__ uint32_t binary_spectrum(const uint16_t *spec, int32_
     return __ballot_sync(kFull, s15 > t);
 }
 
-// WebRtc_ProcessBinarySpectrum (delay_estimator.cc:521-664) with robust validation off, lookahead 0.
-__device__ __forceinline__ int process_binary_spectrum(AecmInstanceState *st, uint32_t near_bits, int lane) {
-    AecmScalars &S = st->s;
-    const int head = S.bin_far_head;
+// WebRtc_ProcessBinarySpectrum (delay_estimator.cc:521-664) with robust validation off, lookahead 0.  The three
+// scalars of the estimator are passed in registers (warp-uniform) and updated in place.
+__device__ __forceinline__ void process_binary_spectrum(AecmInstanceState *st, uint32_t near_bits, int head, int lane,
+                                                        int &minimum_probability, int &last_delay_probability,
+                                                        int &last_delay) {
     int key = 0x7fffffff, worst = 0, any_far = 0;
 #pragma unroll
     for (int p = 0; p < 4; p++) {
@@ -267,17 +268,16 @@ __device__ __forceinline__ int process_binary_spectrum(AecmInstanceState *st, ui
     const int best = min(key >> 7, 32 << 9);
     const int cand = key & 127;
     const int depth = worst - best;
-    if (S.minimum_probability > 8704 && depth > 2816) {  // :593-605
+    if (minimum_probability > 8704 && depth > 2816) {  // :593-605
         const int thr = max(best + 1024, 8704);
-        if (S.minimum_probability > thr) S.minimum_probability = thr;
+        if (minimum_probability > thr) minimum_probability = thr;
     }
-    S.last_delay_probability++;  // :608
-    const bool valid = depth > 1024 && (best < S.minimum_probability || best < S.last_delay_probability);
+    last_delay_probability++;  // :608
+    const bool valid = depth > 1024 && (best < minimum_probability || best < last_delay_probability);
     if (any_far && valid) {  // :643-661
-        S.last_delay = cand;
-        if (best < S.last_delay_probability) S.last_delay_probability = best;
+        last_delay = cand;
+        if (best < last_delay_probability) last_delay_probability = best;
     }
-    return S.last_delay;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -291,7 +291,12 @@ __device__ __forceinline__ void process_block(const Ctx &c, int in_rd, int clean
     AecmScalars &S = st->s;
     const int lane = c.lane;
 
-    if (S.startup_state < 2) S.startup_state = (S.tot_count >= kConvLen) + (S.tot_count >= 2 * kConvLen);  // :420-424
+    // Scalar state discipline: the record's scalars live in shared memory; every lane reads what it needs into
+    // registers, all lanes compute the (warp-uniform) updates redundantly, and lane 0 alone writes them back between
+    // two __syncwarp()s ("commit").  No lane ever reads a scalar that another lane may be writing.
+    int startup_state = S.startup_state;
+    const uint32_t tot_count = S.tot_count;
+    if (startup_state < 2) startup_state = (tot_count >= kConvLen) + (tot_count >= 2 * kConvLen);  // :420-424
 
     // ---- analysis: far, near (noisy) and optionally near (clean), :428-464 ----
     uint32_t dfa_noisy_sum;
@@ -313,12 +318,12 @@ __device__ __forceinline__ void process_block(const Ctx &c, int in_rd, int clean
         q_noisy = qs[1];
         dfa_noisy_sum = sums[1];
     }
-    S.q_noisy_old = S.q_noisy;
-    S.q_noisy = q_noisy;
+    const int q_noisy_old = S.q_noisy;  // :444-447
+    int q_clean, q_clean_old;
     const uint16_t *dfa_clean = sc->dfa_noisy;
     if (!use_clean) {
-        S.q_clean_old = S.q_noisy_old;
-        S.q_clean = S.q_noisy;
+        q_clean_old = q_noisy_old;
+        q_clean = q_noisy;
     } else {
         const int16_t *const olds[1] = {st->d_clean_old};
         uint16_t *const mags[1] = {sc->dfa_clean};
@@ -328,16 +333,14 @@ __device__ __forceinline__ void process_block(const Ctx &c, int in_rd, int clean
         time_to_frequency<1>(
             c, olds, [&](int, int k) { return (int)st->frm_clean[wrap_add(clean_rd, k, AECM_FRM_RING)]; }, mags, cplx,
             sums, qs);
-        S.q_clean_old = S.q_clean;
-        S.q_clean = qs[0];
+        q_clean_old = S.q_clean;
+        q_clean = qs[0];
         dfa_clean = sc->dfa_clean;
     }
-    const int q_clean = S.q_clean, q_clean_old = S.q_clean_old;
 
     // ---- far magnitude history (aecm_core.cc:125-138): one 132-byte row to HBM ----
     int pos = S.far_hist_pos + 1;
     if (pos >= AECM_MAX_DELAY) pos = 0;
-    S.far_hist_pos = pos;
     {
         uint32_t *row = reinterpret_cast<uint32_t *>(c.far_hist + pos * AECM_HIST_ROW);
         const uint32_t *src = reinterpret_cast<const uint32_t *>(sc->xfa);
@@ -346,16 +349,38 @@ __device__ __forceinline__ void process_block(const Ctx &c, int in_rd, int clean
     }
 
     // ---- delay estimation (delay_estimator_wrapper.cc:233-262, 447-476; delay_estimator.cc:369-382) ----
-    {
-        const uint32_t far_bits = binary_spectrum(sc->xfa, st->thr_far, far_q, S.thr_far_init, lane);
-        const int head = S.bin_far_head == 0 ? AECM_MAX_DELAY - 1 : S.bin_far_head - 1;
-        S.bin_far_head = head;
-        st->bin_far[head] = far_bits;
-    }
-    const uint32_t near_bits = binary_spectrum(sc->dfa_noisy, st->thr_near, q_noisy, S.thr_near_init, lane);
+    int thr_far_init = S.thr_far_init, thr_near_init = S.thr_near_init;
+    const int old_head = S.bin_far_head;
+    const int head = old_head == 0 ? AECM_MAX_DELAY - 1 : old_head - 1;
+    const uint32_t far_bits = binary_spectrum(sc->xfa, st->thr_far, far_q, thr_far_init, lane);
+    const uint32_t near_bits = binary_spectrum(sc->dfa_noisy, st->thr_near, q_noisy, thr_near_init, lane);
+    if (lane == 0) st->bin_far[head] = far_bits;
+    int minimum_probability = S.minimum_probability, last_delay_probability = S.last_delay_probability;
+    int last_delay = S.last_delay;
     __syncwarp();
-    int delay = process_binary_spectrum(st, near_bits, lane);
-    if (delay == -2) delay = 0;  // aecm_core_c.cc:479-483
+    process_binary_spectrum(st, near_bits, head, lane, minimum_probability, last_delay_probability, last_delay);
+    const int delay = last_delay == -2 ? 0 : last_delay;  // aecm_core_c.cc:479-483
+    // the energy/VAD section below needs these old values; read them before the first commit
+    const int lh = (S.log_head + AECM_LOG_RING - 1) & (AECM_LOG_RING - 1);
+    int far_e_min = S.far_e_min, far_e_max = S.far_e_max, far_e_maxmin = S.far_e_maxmin, far_e_vad = S.far_e_vad;
+    int far_e_mse = S.far_e_mse, vad_update_count = S.vad_update_count, current_vad = S.current_vad;
+    int first_vad = S.first_vad;
+    __syncwarp();
+    if (lane == 0) {  // commit 1
+        S.startup_state = startup_state;
+        S.q_noisy_old = q_noisy_old;
+        S.q_noisy = q_noisy;
+        S.q_clean_old = q_clean_old;
+        S.q_clean = q_clean;
+        S.far_hist_pos = pos;
+        S.thr_far_init = thr_far_init;
+        S.thr_near_init = thr_near_init;
+        S.bin_far_head = head;
+        S.minimum_probability = minimum_probability;
+        S.last_delay_probability = last_delay_probability;
+        S.last_delay = last_delay;
+        S.log_head = lh;
+    }
 
     // ---- aligned far spectrum (aecm_core.cc:157-172) ----
     const uint16_t *far_spec = sc->xfa;
@@ -374,9 +399,8 @@ __device__ __forceinline__ void process_block(const Ctx &c, int in_rd, int clean
     __syncwarp();
 
     // ---- CalcEnergies (aecm_core.cc:644-755) ----
-    const int lh = (S.log_head + AECM_LOG_RING - 1) & (AECM_LOG_RING - 1);
-    S.log_head = lh;
     const int near_log0 = log_energy_q8(dfa_noisy_sum, q_noisy);
+    int far_log, echo_adapt_log0, echo_stored_log0;
     {
         uint32_t e_far = 0, e_adapt = 0, e_stored = 0;
 #pragma unroll
@@ -394,67 +418,79 @@ __device__ __forceinline__ void process_block(const Ctx &c, int in_rd, int clean
         e_far = __reduce_add_sync(kFull, e_far);
         e_adapt = __reduce_add_sync(kFull, e_adapt);
         e_stored = __reduce_add_sync(kFull, e_stored);
-        S.far_log = log_energy_q8(e_far, zx);
-        st->near_log[lh] = (int16_t)near_log0;
-        st->echo_adapt_log[lh] = (int16_t)log_energy_q8(e_adapt, kResCh16 + zx);
-        st->echo_stored_log[lh] = (int16_t)log_energy_q8(e_stored, kResCh16 + zx);
+        far_log = log_energy_q8(e_far, zx);
+        echo_adapt_log0 = log_energy_q8(e_adapt, kResCh16 + zx);
+        echo_stored_log0 = log_energy_q8(e_stored, kResCh16 + zx);
     }
-    const int far_log = S.far_log;
     if (far_log > kFarEnergyMin) {  // :692-730
         int inc_max = 4, dec_max = 11, inc_min = 11, dec_min = 3;
-        if (S.startup_state == 0) { inc_max = 2; dec_min = 2; inc_min = 8; }
-        S.far_e_min = asym_filt(S.far_e_min, far_log, inc_min, dec_min);
-        S.far_e_max = asym_filt(S.far_e_max, far_log, inc_max, dec_max);
-        S.far_e_maxmin = s16(S.far_e_max - S.far_e_min);
-        int t16 = s16(2560 - S.far_e_min);
+        if (startup_state == 0) { inc_max = 2; dec_min = 2; inc_min = 8; }
+        far_e_min = asym_filt(far_e_min, far_log, inc_min, dec_min);
+        far_e_max = asym_filt(far_e_max, far_log, inc_max, dec_max);
+        far_e_maxmin = s16(far_e_max - far_e_min);
+        int t16 = s16(2560 - far_e_min);
         t16 = t16 > 0 ? s16((t16 * kFarEnergyVadRegion) >> 9) : 0;
         t16 = s16(t16 + kFarEnergyVadRegion);
-        if ((S.startup_state == 0) | (S.vad_update_count > 1024)) {
-            S.far_e_vad = s16(S.far_e_min + t16);
-        } else if (S.far_e_vad > far_log) {
-            S.far_e_vad = s16(S.far_e_vad + ((far_log + t16 - S.far_e_vad) >> 6));
-            S.vad_update_count = 0;
+        if ((startup_state == 0) | (vad_update_count > 1024)) {
+            far_e_vad = s16(far_e_min + t16);
+        } else if (far_e_vad > far_log) {
+            far_e_vad = s16(far_e_vad + ((far_log + t16 - far_e_vad) >> 6));
+            vad_update_count = 0;
         } else {
-            S.vad_update_count = s16(S.vad_update_count + 1);
+            vad_update_count = s16(vad_update_count + 1);
         }
-        S.far_e_mse = s16(S.far_e_vad + (1 << 8));
+        far_e_mse = s16(far_e_vad + (1 << 8));
     }
-    if (far_log > S.far_e_vad) {  // :733-740
-        if ((S.startup_state == 0) | (S.far_e_maxmin > kFarEnergyDiff)) S.current_vad = 1;
+    if (far_log > far_e_vad) {  // :733-740
+        if ((startup_state == 0) | (far_e_maxmin > kFarEnergyDiff)) current_vad = 1;
     } else {
-        S.current_vad = 0;
+        current_vad = 0;
     }
-    if (S.current_vad && S.first_vad) {  // :741-754
-        S.first_vad = 0;
-        __syncwarp();
-        if ((int)st->echo_adapt_log[lh] > near_log0) {
+    if (current_vad && first_vad) {  // :741-754
+        first_vad = 0;
+        if (echo_adapt_log0 > near_log0) {
 #pragma unroll
             for (int p = 0; p < 3; p++) {
                 const int i = lane + 32 * p;
                 if (i < AECM_BINS) st->ch_adapt16[i] = (int16_t)(st->ch_adapt16[i] >> 3);
             }
-            __syncwarp();
-            st->echo_adapt_log[lh] = (int16_t)(st->echo_adapt_log[lh] - (3 << 8));
-            S.first_vad = 1;
+            echo_adapt_log0 = s16(echo_adapt_log0 - (3 << 8));
+            first_vad = 1;
         }
     }
 
     // ---- CalcStepSize (aecm_core.cc:767-794) ----
     int mu = kMuMax;
-    if (!S.current_vad) {
+    if (!current_vad) {
         mu = 0;
-    } else if (S.startup_state > 0) {
-        if (S.far_e_min >= S.far_e_max) {
+    } else if (startup_state > 0) {
+        if (far_e_min >= far_e_max) {
             mu = kMuMin;
         } else {
-            const int t16 = s16(far_log - S.far_e_min);
-            const int den = S.far_e_maxmin;
+            const int t16 = s16(far_log - far_e_min);
+            const int den = far_e_maxmin;
             const int t32 = den != 0 ? (t16 * kMuDiff) / den : 0x7fffffff;
             mu = s16(kMuMin - 1 - s16(t32));
         }
         if (mu < kMuMax) mu = kMuMax;
     }
-    S.tot_count++;  // aecm_core_c.cc:506
+    __syncwarp();
+    if (lane == 0) {  // commit 2
+        S.far_log = far_log;
+        st->near_log[lh] = (int16_t)near_log0;
+        st->echo_adapt_log[lh] = (int16_t)echo_adapt_log0;
+        st->echo_stored_log[lh] = (int16_t)echo_stored_log0;
+        S.far_e_min = far_e_min;
+        S.far_e_max = far_e_max;
+        S.far_e_maxmin = far_e_maxmin;
+        S.far_e_vad = far_e_vad;
+        S.far_e_mse = far_e_mse;
+        S.vad_update_count = vad_update_count;
+        S.current_vad = current_vad;
+        S.first_vad = first_vad;
+        S.tot_count = tot_count + 1;  // aecm_core_c.cc:506
+    }
+    __syncwarp();
 
     // ---- UpdateChannel (aecm_core.cc:810-986) ----
     const int q_n = q_noisy;
@@ -514,16 +550,18 @@ __device__ __forceinline__ void process_block(const Ctx &c, int in_rd, int clean
         }
         __syncwarp();
     }
+    // scalars of the channel-store decision and of the suppression gain (last written by the previous block's commit 3)
+    int mse_channel_count = S.mse_channel_count, mse_threshold = S.mse_threshold;
+    int mse_stored_old = S.mse_stored_old, mse_adapt_old = S.mse_adapt_old;
     bool do_store = false;
-    if ((S.startup_state == 0) & (S.current_vad != 0)) {  // :926-929
+    if ((startup_state == 0) & (current_vad != 0)) {  // :926-929
         do_store = true;
     } else {
-        if (far_log < S.far_e_mse) S.mse_channel_count = 0;
-        else S.mse_channel_count = s16(S.mse_channel_count + 1);
-        if (S.mse_channel_count >= kMinMseCount + 10) {  // :937-983
-            __syncwarp();
+        if (far_log < far_e_mse) mse_channel_count = 0;
+        else mse_channel_count = s16(mse_channel_count + 1);
+        if (mse_channel_count >= kMinMseCount + 10) {  // :937-983
             int ds = 0, da = 0;
-            if (lane < kMinMseCount) {
+            if (lane < kMinMseCount) {  // the 20 newest log energies (entry lh was committed above)
                 const int k = (lh + lane) & (AECM_LOG_RING - 1);
                 const int nl = st->near_log[k];
                 ds = abs((int)st->echo_stored_log[k] - nl);
@@ -532,7 +570,7 @@ __device__ __forceinline__ void process_block(const Ctx &c, int in_rd, int clean
             const int mse_stored = __reduce_add_sync(kFull, ds);
             const int mse_adapt = __reduce_add_sync(kFull, da);
             if (((mse_stored << kMseResolution) < (kMinMseDiff * mse_adapt)) &
-                ((S.mse_stored_old << kMseResolution) < (kMinMseDiff * S.mse_adapt_old))) {
+                ((mse_stored_old << kMseResolution) < (kMinMseDiff * mse_adapt_old))) {
                 // ResetAdaptiveChannel, aecm_core.cc:308-323
 #pragma unroll
                 for (int p = 0; p < 3; p++) {
@@ -543,19 +581,19 @@ __device__ __forceinline__ void process_block(const Ctx &c, int in_rd, int clean
                         st->ch_adapt32[i] = (int)((uint32_t)v << 16);
                     }
                 }
-            } else if (((kMinMseDiff * mse_stored) > (mse_adapt << kMseResolution)) & (mse_adapt < S.mse_threshold) &
-                       (S.mse_adapt_old < S.mse_threshold)) {
+            } else if (((kMinMseDiff * mse_stored) > (mse_adapt << kMseResolution)) & (mse_adapt < mse_threshold) &
+                       (mse_adapt_old < mse_threshold)) {
                 do_store = true;
-                if (S.mse_threshold == 0x7fffffff) {
-                    S.mse_threshold = mse_adapt + S.mse_adapt_old;
+                if (mse_threshold == 0x7fffffff) {
+                    mse_threshold = mse_adapt + mse_adapt_old;
                 } else {
-                    const int scaled = S.mse_threshold * 5 / 8;
-                    S.mse_threshold += ((mse_adapt - scaled) * 205) >> 8;
+                    const int scaled = mse_threshold * 5 / 8;
+                    mse_threshold += ((mse_adapt - scaled) * 205) >> 8;
                 }
             }
-            S.mse_channel_count = 0;
-            S.mse_stored_old = mse_stored;
-            S.mse_adapt_old = mse_adapt;
+            mse_channel_count = 0;
+            mse_stored_old = mse_stored;
+            mse_adapt_old = mse_adapt;
         }
     }
     if (do_store) {  // StoreAdaptiveChannel, aecm_core.cc:286-306
@@ -569,33 +607,41 @@ __device__ __forceinline__ void process_block(const Ctx &c, int in_rd, int clean
             }
         }
     }
-    __syncwarp();
 
     // ---- CalcSuppressionGain (aecm_core.cc:1000-1052) ----
-    int sup_gain;
+    int sup_gain_old = S.sup_gain_old, sup_gain = S.sup_gain;
     {
+        const int sup_a = S.sup_a, sup_d = S.sup_d, sup_diff_ab = S.sup_diff_ab, sup_diff_bd = S.sup_diff_bd;
         int g = kSupGainDefault;
-        if (!S.current_vad) {
+        if (!current_vad) {
             g = 0;
         } else {
-            const int t16 = s16((int)st->near_log[lh] - (int)st->echo_stored_log[lh]);
+            const int t16 = s16(near_log0 - echo_stored_log0);
             const int de = t16 >= 0 ? t16 : s16(-t16);
             if (de < kEnergyDevTol) {
                 if (de < kSupGainEpcDt) {
-                    const int t32 = S.sup_diff_ab * de + (kSupGainEpcDt >> 1);
-                    g = s16(S.sup_a - s16(t32 / kSupGainEpcDt));
+                    const int t32 = sup_diff_ab * de + (kSupGainEpcDt >> 1);
+                    g = s16(sup_a - s16(t32 / kSupGainEpcDt));
                 } else {
-                    const int t32 = S.sup_diff_bd * (kEnergyDevTol - de) + ((kEnergyDevTol - kSupGainEpcDt) >> 1);
-                    g = s16(S.sup_d + s16(t32 / (kEnergyDevTol - kSupGainEpcDt)));
+                    const int t32 = sup_diff_bd * (kEnergyDevTol - de) + ((kEnergyDevTol - kSupGainEpcDt) >> 1);
+                    g = s16(sup_d + s16(t32 / (kEnergyDevTol - kSupGainEpcDt)));
                 }
             } else {
-                g = S.sup_d;
+                g = sup_d;
             }
         }
-        const int t = g > S.sup_gain_old ? g : S.sup_gain_old;
-        S.sup_gain_old = g;
-        S.sup_gain = s16(S.sup_gain + s16((t - S.sup_gain) >> 4));
-        sup_gain = S.sup_gain;
+        const int t = g > sup_gain_old ? g : sup_gain_old;
+        sup_gain_old = g;
+        sup_gain = s16(sup_gain + s16((t - sup_gain) >> 4));
+    }
+    __syncwarp();
+    if (lane == 0) {  // commit 3
+        S.mse_channel_count = mse_channel_count;
+        S.mse_threshold = mse_threshold;
+        S.mse_stored_old = mse_stored_old;
+        S.mse_adapt_old = mse_adapt_old;
+        S.sup_gain_old = sup_gain_old;
+        S.sup_gain = sup_gain;
     }
 
     // ---- Wiener gain per bin (aecm_core_c.cc:517-615) ----
@@ -661,7 +707,7 @@ __device__ __forceinline__ void process_block(const Ctx &c, int in_rd, int clean
         }
     }
     num_pos = __reduce_add_sync(kFull, num_pos);
-    if (S.mult == 2) {  // wideband only, :618-648
+    if (S.mult == 2) {  // wideband only, :618-648 (mult is only written by Init)
         int part = 0;
 #pragma unroll
         for (int p = 0; p < 3; p++) hnl[p] = (hnl[p] * hnl[p]) >> 14;
@@ -693,11 +739,13 @@ __device__ __forceinline__ void process_block(const Ctx &c, int in_rd, int clean
     }
 
     // ---- ComfortNoise (aecm_core_c.cc:52-164) ----
-    if (S.cng_mode == 1) {
+    if (S.cng_mode == 1) {  // cng_mode is only written by set_config
+        // noise_est_ctr / seed were last written by the previous block's commit 4
+        int noise_est_ctr = S.noise_est_ctr;
+        const uint32_t seed = S.seed;
         const int sh = 15 - q_clean;
         int track;
-        if (S.noise_est_ctr < 100) { S.noise_est_ctr++; track = 6; } else { track = 9; }
-        const uint32_t seed = S.seed;
+        if (noise_est_ctr < 100) { noise_est_ctr++; track = 6; } else { track = 9; }
 #pragma unroll
         for (int p = 0; p < 3; p++) {
             const int i = lane + 32 * p;
@@ -740,7 +788,11 @@ __device__ __forceinline__ void process_block(const Ctx &c, int in_rd, int clean
                 }
             }
         }
-        S.seed = (kLcgJump.mul[63] * seed + kLcgJump.add[63]) & 0x7fffffffu;  // 64 draws per block, :143
+        __syncwarp();
+        if (lane == 0) {  // commit 4 (nobody reads these again in this block)
+            S.noise_est_ctr = noise_est_ctr;
+            S.seed = (kLcgJump.mul[63] * seed + kLcgJump.add[63]) & 0x7fffffffu;  // 64 draws per block, :143
+        }
     }
 
     // ---- InverseFFTAndWindow (aecm_core_c.cc:193-246, real_fft.c:74-102) ----
@@ -820,9 +872,13 @@ __device__ __forceinline__ void process_frame(const Ctx &c, bool live, int far_i
     AecmInstanceState *st = c.st;
     AecmScalars &S = st->s;
     const int lane = c.lane;
-    if (live) {  // WebRtc_WriteBuffer x2/x3, :520-524 (a full FIFO drops the excess, ring_buffer.c:150-152)
-        const int n = min(AECM_FRAME_LEN, AECM_FRM_RING - S.frm_in_cnt);
-        const int wr = wrap_add(S.frm_in_rd, S.frm_in_cnt, AECM_FRM_RING);
+    // FIFO cursors are read into registers (warp-uniform), updated there, and committed by lane 0
+    if (live) {
+        const int in_rd = S.frm_in_rd, clean_rd = S.frm_clean_rd;
+        int in_cnt = S.frm_in_cnt, clean_cnt = S.frm_clean_cnt;
+        // WebRtc_WriteBuffer x2/x3, :520-524 (a full FIFO drops the excess, ring_buffer.c:150-152)
+        const int n = min(AECM_FRAME_LEN, AECM_FRM_RING - in_cnt);
+        const int wr = wrap_add(in_rd, in_cnt, AECM_FRM_RING);
         if (n == AECM_FRAME_LEN && ((wr | far_idx) & 1) == 0 && word_aligned(near80)) {
             const uint32_t *nw = reinterpret_cast<const uint32_t *>(near80);
             const uint32_t *ring = reinterpret_cast<const uint32_t *>(c.far_ring);
@@ -853,12 +909,17 @@ __device__ __forceinline__ void process_frame(const Ctx &c, bool live, int far_i
                 st->frm_near[w] = near80[k];
             }
         }
-        S.frm_in_cnt += n;
+        in_cnt += n;
         if (clean80) {
-            const int nc = min(AECM_FRAME_LEN, AECM_FRM_RING - S.frm_clean_cnt);
-            const int wc = wrap_add(S.frm_clean_rd, S.frm_clean_cnt, AECM_FRM_RING);
+            const int nc = min(AECM_FRAME_LEN, AECM_FRM_RING - clean_cnt);
+            const int wc = wrap_add(clean_rd, clean_cnt, AECM_FRM_RING);
             for (int k = lane; k < nc; k += 32) st->frm_clean[wrap_add(wc, k, AECM_FRM_RING)] = clean80[k];
-            S.frm_clean_cnt += nc;
+            clean_cnt += nc;
+        }
+        __syncwarp();
+        if (lane == 0) {  // commit the input cursors; nothing is kept in registers across a block
+            S.frm_in_cnt = in_cnt;
+            S.frm_clean_cnt = clean_cnt;
         }
         __syncwarp();
     }
@@ -867,35 +928,47 @@ __device__ __forceinline__ void process_frame(const Ctx &c, bool live, int far_i
     for (int blk = 0; blk < 2; blk++) {
         cta_rendezvous();
         if (live && S.frm_in_cnt >= AECM_PART_LEN) {
-            const int in_rd = S.frm_in_rd;
-            const int clean_rd = S.frm_clean_rd;
-            const int n = min(AECM_PART_LEN, AECM_FRM_RING - S.frm_out_cnt);
-            const int wr = wrap_add(S.frm_out_rd, S.frm_out_cnt, AECM_FRM_RING);
-            process_block(c, in_rd, clean_rd, clean80 != nullptr, wr, n);
-            fifo_move(S.frm_in_rd, S.frm_in_cnt, AECM_FRM_RING, AECM_PART_LEN);
-            if (clean80) fifo_move(S.frm_clean_rd, S.frm_clean_cnt, AECM_FRM_RING, AECM_PART_LEN);
-            S.frm_out_cnt += n;
+            {
+                const int o_rd = S.frm_out_rd, o_cnt = S.frm_out_cnt;
+                process_block(c, S.frm_in_rd, S.frm_clean_rd, clean80 != nullptr, wrap_add(o_rd, o_cnt, AECM_FRM_RING),
+                              min(AECM_PART_LEN, AECM_FRM_RING - o_cnt));
+            }
+            int i_rd = S.frm_in_rd, i_cnt = S.frm_in_cnt, c_rd = S.frm_clean_rd, c_cnt = S.frm_clean_cnt;
+            const int o_cnt = S.frm_out_cnt + min(AECM_PART_LEN, AECM_FRM_RING - S.frm_out_cnt);
+            fifo_move(i_rd, i_cnt, AECM_FRM_RING, AECM_PART_LEN);
+            if (clean80) fifo_move(c_rd, c_cnt, AECM_FRM_RING, AECM_PART_LEN);
+            __syncwarp();
+            if (lane == 0) {
+                S.frm_in_rd = i_rd; S.frm_in_cnt = i_cnt;
+                S.frm_clean_rd = c_rd; S.frm_clean_cnt = c_cnt;
+                S.frm_out_cnt = o_cnt;
+            }
             __syncwarp();
         }
     }
     if (!live) return;
-    if (S.frm_out_cnt < AECM_FRAME_LEN)  // :559-562: rewind, re-emitting already delivered samples
-        fifo_move(S.frm_out_rd, S.frm_out_cnt, AECM_FRM_RING, S.frm_out_cnt - AECM_FRAME_LEN);
+    int out_rd = S.frm_out_rd, out_cnt = S.frm_out_cnt;
+    if (out_cnt < AECM_FRAME_LEN)  // :559-562: rewind, re-emitting already delivered samples
+        fifo_move(out_rd, out_cnt, AECM_FRM_RING, out_cnt - AECM_FRAME_LEN);
     {
-        const int n = min(AECM_FRAME_LEN, S.frm_out_cnt);
-        const int rd = S.frm_out_rd;
-        if (n == AECM_FRAME_LEN && (rd & 1) == 0 && word_aligned(out80)) {
+        const int n = min(AECM_FRAME_LEN, out_cnt);
+        if (n == AECM_FRAME_LEN && (out_rd & 1) == 0 && word_aligned(out80)) {
             uint32_t *ow = reinterpret_cast<uint32_t *>(out80);
             const uint32_t *fo = reinterpret_cast<const uint32_t *>(st->frm_out);
 #pragma unroll
             for (int h = 0; h < 2; h++) {
                 const int k = lane + 32 * h;
-                if (k < AECM_FRAME_LEN / 2) ow[k] = fo[wrap_add(rd >> 1, k, AECM_FRM_RING / 2)];
+                if (k < AECM_FRAME_LEN / 2) ow[k] = fo[wrap_add(out_rd >> 1, k, AECM_FRM_RING / 2)];
             }
         } else {
-            for (int k = lane; k < n; k += 32) out80[k] = st->frm_out[wrap_add(rd, k, AECM_FRM_RING)];
+            for (int k = lane; k < n; k += 32) out80[k] = st->frm_out[wrap_add(out_rd, k, AECM_FRM_RING)];
         }
-        fifo_move(S.frm_out_rd, S.frm_out_cnt, AECM_FRM_RING, n);
+        fifo_move(out_rd, out_cnt, AECM_FRM_RING, n);
+    }
+    __syncwarp();
+    if (lane == 0) {  // commit the output cursor
+        S.frm_out_rd = out_rd;
+        S.frm_out_cnt = out_cnt;
     }
     __syncwarp();
 }
@@ -906,18 +979,20 @@ __device__ __forceinline__ void process_frame(const Ctx &c, bool live, int far_i
 __device__ __forceinline__ int api_buffer_farend(const Ctx &c, const int16_t *far, int n) {
     AecmScalars &S = c.st->s;
     if (S.init_flag != AECM_INIT_MAGIC) return AECM_UNINITIALIZED_ERROR;
+    int far_rd = S.far_rd, far_cnt = S.far_cnt;
+    bool stuffed = false;
     if (!S.ec_startup) {  // WebRtcAecm_DelayComp, :575-594
-        const int n_far = S.far_cnt;
-        const int n_snd = S.ms_in_snd_card_buf * 8 * S.mult;
-        if (n_snd - n_far > 4 * AECM_PART_LEN - AECM_FRAME_LEN * S.mult) {
-            int add = max((n_snd >> 1) - n_far, AECM_FRAME_LEN);
+        const int mult = S.mult;
+        const int n_snd = S.ms_in_snd_card_buf * 8 * mult;
+        if (n_snd - far_cnt > 4 * AECM_PART_LEN - AECM_FRAME_LEN * mult) {
+            int add = max((n_snd >> 1) - far_cnt, AECM_FRAME_LEN);
             add = min(add, 10 * AECM_FRAME_LEN);
-            fifo_move(S.far_rd, S.far_cnt, AECM_FAR_RING, -add);
-            S.delay_change = 1;
+            fifo_move(far_rd, far_cnt, AECM_FAR_RING, -add);
+            stuffed = true;
         }
     }
-    const int w = min(n, AECM_FAR_RING - S.far_cnt);
-    int wr = S.far_rd + S.far_cnt;
+    const int w = min(n, AECM_FAR_RING - far_cnt);
+    int wr = far_rd + far_cnt;
     if (wr >= AECM_FAR_RING) wr -= AECM_FAR_RING;
     if (((wr | w) & 1) == 0 && word_aligned(far)) {
         const uint32_t *src = reinterpret_cast<const uint32_t *>(far);
@@ -926,30 +1001,40 @@ __device__ __forceinline__ int api_buffer_farend(const Ctx &c, const int16_t *fa
     } else {
         for (int k = c.lane; k < w; k += 32) c.far_ring[wrap_add(wr, k, AECM_FAR_RING)] = far[k];
     }
-    S.far_cnt += w;
+    far_cnt += w;
+    __syncwarp();
+    if (c.lane == 0) {
+        S.far_rd = far_rd;
+        S.far_cnt = far_cnt;
+        if (stuffed) S.delay_change = 1;
+    }
     __syncwarp();
     return 0;
 }
 
-__device__ __forceinline__ void est_buf_delay(AecmScalars &S) {  // echo_control_mobile.cc:534-573
-    const int n_far = s16(S.far_cnt);
-    const int n_snd = s16(S.ms_in_snd_card_buf * 8 * S.mult);
+// WebRtcAecm_EstBufDelay (echo_control_mobile.cc:534-573) on register copies of the wrapper scalars
+struct DelayRegs {
+    int far_rd, far_cnt, filt_delay, known_delay, last_delay_diff, time_for_delay_change;
+};
+__device__ __forceinline__ void est_buf_delay(DelayRegs &d, int ms, int mult) {
+    const int n_far = s16(d.far_cnt);
+    const int n_snd = s16(ms * 8 * mult);
     int delay_new = s16(n_snd - n_far);
     if (delay_new < AECM_FRAME_LEN) {
-        fifo_move(S.far_rd, S.far_cnt, AECM_FAR_RING, AECM_FRAME_LEN);
+        fifo_move(d.far_rd, d.far_cnt, AECM_FAR_RING, AECM_FRAME_LEN);
         delay_new = s16(delay_new + AECM_FRAME_LEN);
     }
-    S.filt_delay = s16(max(0, (8 * S.filt_delay + 2 * delay_new) / 10));
-    const int diff = s16(S.filt_delay - S.wrapper_known_delay);
+    d.filt_delay = s16(max(0, (8 * d.filt_delay + 2 * delay_new) / 10));
+    const int diff = s16(d.filt_delay - d.known_delay);
     if (diff > 224) {
-        if (S.last_delay_diff < 96) S.time_for_delay_change = 0; else S.time_for_delay_change++;
-    } else if (diff < 96 && S.wrapper_known_delay > 0) {
-        if (S.last_delay_diff > 224) S.time_for_delay_change = 0; else S.time_for_delay_change++;
+        if (d.last_delay_diff < 96) d.time_for_delay_change = 0; else d.time_for_delay_change++;
+    } else if (diff < 96 && d.known_delay > 0) {
+        if (d.last_delay_diff > 224) d.time_for_delay_change = 0; else d.time_for_delay_change++;
     } else {
-        S.time_for_delay_change = 0;
+        d.time_for_delay_change = 0;
     }
-    S.last_delay_diff = diff;
-    if (S.time_for_delay_change > 25) S.wrapper_known_delay = max(S.filt_delay - 160, 0);  // never forwarded (:390-391)
+    d.last_delay_diff = diff;
+    if (d.time_for_delay_change > 25) d.known_delay = max(d.filt_delay - 160, 0);  // never forwarded (:390-391)
 }
 
 // `live` = the warp owns an instance and its BufferFarend/Process calls are to be executed; dead warps only keep
@@ -964,55 +1049,83 @@ __device__ __forceinline__ int api_process(const Ctx &c, bool live, const int16_
     if (live) {
         if (S.init_flag != AECM_INIT_MAGIC) {
             ret = AECM_UNINITIALIZED_ERROR;
-        } else {
-            if (ms < 0) { ms = 0; ret = AECM_BAD_PARAMETER_WARNING; }          // :272-278
-            else if (ms > 500) { ms = 500; ret = AECM_BAD_PARAMETER_WARNING; }
-            ms += 10;
-            S.ms_in_snd_card_buf = ms;
-            const int n_blocks10ms = n_frames / S.mult;
-            if (S.ec_startup) {  // :285-356
-                const int16_t *src = near_clean ? near_clean : near_noisy;
-                if (out != src)
-                    for (int k = lane; k < n; k += 32) out[k] = src[k];
-                const int filled = s16(S.far_cnt) / AECM_FRAME_LEN;
-                if (S.check_buff_size) {
-                    S.check_buf_size_ctr = s16(S.check_buf_size_ctr + 1);
-                    if (S.counter == 0) { S.first_val = ms; S.sum = 0; }
-                    const int dev = abs(S.first_val - ms);
-                    const double tol = 0.2 * ms > 8 ? 0.2 * ms : 8;  // :312-313, a double comparison in the reference
-                    if ((double)dev < tol) { S.sum = s16(S.sum + ms); S.counter = s16(S.counter + 1); }
-                    else S.counter = 0;
-                    if (S.counter * n_blocks10ms >= 6) {
-                        S.buf_size_start = s16(min((3 * S.sum * S.mult) / (S.counter * 40), 50));
-                        S.check_buff_size = 0;
-                    }
-                    if (S.check_buf_size_ctr * n_blocks10ms > 50) {
-                        S.buf_size_start = s16(min((3 * ms * S.mult) / 40, 50));
-                        S.check_buff_size = 0;
-                    }
+            live = false;
+        }
+    }
+    if (live) {
+        if (ms < 0) { ms = 0; ret = AECM_BAD_PARAMETER_WARNING; }          // :272-278
+        else if (ms > 500) { ms = 500; ret = AECM_BAD_PARAMETER_WARNING; }
+        ms += 10;
+        const int mult = S.mult;
+        const int n_blocks10ms = n_frames / mult;
+        int ec_startup = S.ec_startup;
+        if (ec_startup) {  // :285-356
+            const int16_t *src = near_clean ? near_clean : near_noisy;
+            if (out != src)
+                for (int k = lane; k < n; k += 32) out[k] = src[k];
+            int far_rd = S.far_rd, far_cnt = S.far_cnt;
+            const int filled = s16(far_cnt) / AECM_FRAME_LEN;
+            int check_buff_size = S.check_buff_size, check_buf_size_ctr = S.check_buf_size_ctr;
+            int counter = S.counter, first_val = S.first_val, sum = S.sum, buf_size_start = S.buf_size_start;
+            if (check_buff_size) {
+                check_buf_size_ctr = s16(check_buf_size_ctr + 1);
+                if (counter == 0) { first_val = ms; sum = 0; }
+                const int dev = abs(first_val - ms);
+                const double tol = 0.2 * ms > 8 ? 0.2 * ms : 8;  // :312-313, a double comparison in the reference
+                if ((double)dev < tol) { sum = s16(sum + ms); counter = s16(counter + 1); }
+                else counter = 0;
+                if (counter * n_blocks10ms >= 6) {
+                    buf_size_start = s16(min((3 * sum * mult) / (counter * 40), 50));
+                    check_buff_size = 0;
                 }
-                if (!S.check_buff_size) {
-                    if (filled == S.buf_size_start) {
-                        S.ec_startup = 0;
-                    } else if (filled > S.buf_size_start) {
-                        fifo_move(S.far_rd, S.far_cnt, AECM_FAR_RING, S.far_cnt - S.buf_size_start * AECM_FRAME_LEN);
-                        S.ec_startup = 0;
-                    }
+                if (check_buf_size_ctr * n_blocks10ms > 50) {
+                    buf_size_start = s16(min((3 * ms * mult) / 40, 50));
+                    check_buff_size = 0;
                 }
-            } else {
-                processing = true;
             }
+            if (!check_buff_size) {
+                if (filled == buf_size_start) {
+                    ec_startup = 0;
+                } else if (filled > buf_size_start) {
+                    fifo_move(far_rd, far_cnt, AECM_FAR_RING, far_cnt - buf_size_start * AECM_FRAME_LEN);
+                    ec_startup = 0;
+                }
+            }
+            __syncwarp();
+            if (lane == 0) {
+                S.ms_in_snd_card_buf = ms;
+                S.check_buff_size = check_buff_size; S.check_buf_size_ctr = check_buf_size_ctr;
+                S.counter = counter; S.first_val = first_val; S.sum = sum; S.buf_size_start = buf_size_start;
+                S.ec_startup = ec_startup;
+                S.far_rd = far_rd; S.far_cnt = far_cnt;
+            }
+            __syncwarp();
+        } else {
+            processing = true;
         }
     }
     for (int i = 0; i < n_frames; i++) {  // :358-397
         int far_idx = -1;
-        if (processing) {
-            const int filled = s16(S.far_cnt) / AECM_FRAME_LEN;
+        if (processing) {  // wrapper bookkeeping of this frame on register copies, committed before the frame is processed
+            DelayRegs d;
+            d.far_rd = S.far_rd; d.far_cnt = S.far_cnt;
+            d.filt_delay = S.filt_delay; d.known_delay = S.wrapper_known_delay;
+            d.last_delay_diff = S.last_delay_diff; d.time_for_delay_change = S.time_for_delay_change;
+            const int fs = S.fs;
+            const int filled = s16(d.far_cnt) / AECM_FRAME_LEN;
             if (filled > 0) {  // WebRtc_ReadBuffer of 80 samples
-                far_idx = S.far_rd;
-                fifo_move(S.far_rd, S.far_cnt, AECM_FAR_RING, AECM_FRAME_LEN);
+                far_idx = d.far_rd;
+                fifo_move(d.far_rd, d.far_cnt, AECM_FAR_RING, AECM_FRAME_LEN);
             }
-            if ((i == 0 && S.fs == 8000) || (i == 1 && S.fs == 16000)) est_buf_delay(S);
+            if ((i == 0 && fs == 8000) || (i == 1 && fs == 16000)) est_buf_delay(d, ms, S.mult);
+            __syncwarp();
+            if (lane == 0) {
+                S.ms_in_snd_card_buf = ms;
+                S.far_rd = d.far_rd; S.far_cnt = d.far_cnt;
+                S.filt_delay = d.filt_delay; S.wrapper_known_delay = d.known_delay;
+                S.last_delay_diff = d.last_delay_diff; S.time_for_delay_change = d.time_for_delay_change;
+            }
+            __syncwarp();
         }
         process_frame(c, processing, far_idx, i, near_noisy + AECM_FRAME_LEN * i,
                       near_clean ? near_clean + AECM_FRAME_LEN * i : nullptr, out + AECM_FRAME_LEN * i);
