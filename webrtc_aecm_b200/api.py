@@ -55,14 +55,14 @@ class Scalars(C.Structure):
 
 class InstanceState(C.Structure):
     """``AecmInstanceState`` of csrc/aecm_state.h (introspection only)."""
-    _fields_ = [("ch_adapt32", C.c_int32 * 68), ("echo_filt", C.c_int32 * 68), ("noise_est", C.c_int32 * 68),
-                ("ch_stored", C.c_int16 * 72), ("ch_adapt16", C.c_int16 * 72), ("near_filt", C.c_int16 * 72),
-                ("noise_low_ctr", C.c_uint8 * 80), ("noise_high_ctr", C.c_uint8 * 80), ("x_old", C.c_int16 * 64),
+    _fields_ = [("s", Scalars), ("farend_old", (C.c_int16 * 80) * 2), ("frm_far", C.c_int16 * 144),
+                ("frm_near", C.c_int16 * 144), ("frm_out", C.c_int16 * 144), ("x_old", C.c_int16 * 64),
                 ("d_noisy_old", C.c_int16 * 64), ("out_ola", C.c_int16 * 64), ("thr_far", C.c_int32 * 32),
                 ("thr_near", C.c_int32 * 32), ("bin_far", C.c_uint32 * 104), ("mean_bit_counts", C.c_int32 * 104),
                 ("near_log", C.c_int16 * 32), ("echo_adapt_log", C.c_int16 * 32), ("echo_stored_log", C.c_int16 * 32),
-                ("frm_far", C.c_int16 * 144), ("frm_near", C.c_int16 * 144), ("frm_out", C.c_int16 * 144),
-                ("farend_old", (C.c_int16 * 80) * 2), ("s", Scalars), ("d_clean_old", C.c_int16 * 64),
+                ("ch_adapt32", C.c_int32 * 68), ("echo_filt", C.c_int32 * 68), ("noise_est", C.c_int32 * 68),
+                ("ch_stored", C.c_int16 * 72), ("ch_adapt16", C.c_int16 * 72), ("near_filt", C.c_int16 * 72),
+                ("noise_low_ctr", C.c_uint8 * 80), ("noise_high_ctr", C.c_uint8 * 80), ("d_clean_old", C.c_int16 * 64),
                 ("frm_clean", C.c_int16 * 144)]
 
 

@@ -1,7 +1,7 @@
 // aecm_kernels.cu -- the batched AECM engine's device code for sm_100a.
 //
 // One warp owns one AECM instance.  A launch stages the instance record (aecm_state.h) from HBM into
-// shared memory with 128-bit coalesced accesses, runs `n_calls` fused 10 ms API calls
+// shared memory with one bulk async copy per warp (TMA unit, mbarrier-signalled), runs `n_calls` fused 10 ms API calls
 // (BufferFarend + Process: far-end jitter FIFO -> 80-sample frames -> 64-sample blocks -> block DSP) and
 // writes the record back.  All arithmetic is int16/int32 Q-format and bit-exact with the reference's
 // generic C path; every stage cites the reference lines (relative to /root/reference/aecm) it implements.
@@ -82,6 +82,35 @@ constexpr LaneTables make_lane_tables() {
 }
 __device__ const LaneTables kLaneTables = make_lane_tables();
 
+// Exact signed division by d = 2..65 (the NLMS normalisation by bin index + 1, aecm_core.cc:904) without a divide:
+// for 0 <= n <= 2^31 and 2^s <= d < 2^(s+1), floor(n / d) = (n * M) >> (32 + s') with M = ceil(2^(32+s') / d) < 2^32,
+// s' = s for non powers of two and s - 1 for powers of two (then M = 2^31 exactly).  Truncation toward zero for
+// negative dividends is restored by dividing |n|.
+struct DivTable {
+    uint32_t mul[66];
+    int32_t shift[66];
+};
+constexpr DivTable make_div_table() {
+    DivTable t{};
+    for (int d = 2; d <= 65; d++) {
+        int s = 0;
+        while ((2 << s) <= d) s++;          // 2^s <= d < 2^(s+1)
+        const bool pow2 = (1 << s) == d;
+        const int sp = pow2 ? s - 1 : s;
+        const unsigned long long num = 1ull << (32 + sp);
+        t.mul[d] = (uint32_t)((num + (unsigned)d - 1) / (unsigned)d);
+        t.shift[d] = sp;
+    }
+    return t;
+}
+__device__ const DivTable kDivTable = make_div_table();
+__device__ __forceinline__ int div_by_bin(int n, int d) {  // d = bin index + 1 in [1, 65]
+    if (d == 1) return n;
+    const uint32_t a = (uint32_t)abs(n);
+    const uint32_t q = __umulhi(a, __ldg(&kDivTable.mul[d])) >> __ldg(&kDivTable.shift[d]);
+    return n < 0 ? -(int)q : (int)q;
+}
+
 __device__ __forceinline__ const int2 *twiddle_table() { return reinterpret_cast<const int2 *>(kAecmTwiddleCS); }
 __device__ __forceinline__ int hann_q14(int i) { return __ldg(&kAecmSqrtHanningQ14[i]); }
 
@@ -90,8 +119,8 @@ struct __align__(16) WarpScratch {
     uint32_t dfw[68];      // near (or clean) spectrum after the sign flip of aecm_core_c.cc:188-190
     int32_t echo_est[68];
     uint16_t xfa[72], dfa_noisy[72], dfa_clean[72], far_row[72];
-    uint64_t mbar;         // mbarrier of the record's bulk load
-    uint64_t pad_;
+    uint64_t mbar_a;       // mbarriers of the record's two bulk loads (part A: scalars/FIFOs, part B: the rest)
+    uint64_t mbar_b;
 };
 
 struct Ctx {
@@ -101,6 +130,20 @@ struct Ctx {
     int16_t *far_ring;      // this instance's 4000-sample jitter FIFO in HBM
     int lane;
 };
+
+// wait for a bulk load (phase 0 of its mbarrier); returns at once when the data already arrived
+__device__ __forceinline__ void mbar_wait(uint64_t *bar) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_RECORD:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], 0;\n"
+        "@p bra DONE_RECORD;\n"
+        "bra WAIT_RECORD;\n"
+        "DONE_RECORD:\n"
+        "}\n" ::"r"((uint32_t)__cvta_generic_to_shared(bar))
+        : "memory");
+}
 
 // ------------------------------------------------------------------------------------------------
 // scalar primitives (spl_inl.h, signal_processing_library.{h,cc})
@@ -349,6 +392,7 @@ __device__ __forceinline__ void process_block(const Ctx &c, int in_rd, int clean
     }
 
     // ---- delay estimation (delay_estimator_wrapper.cc:233-262, 447-476; delay_estimator.cc:369-382) ----
+    mbar_wait(&sc->mbar_b);  // everything from here on lives in part B of the record (its copy ran behind the FFTs)
     int thr_far_init = S.thr_far_init, thr_near_init = S.thr_near_init;
     const int old_head = S.bin_far_head;
     const int head = old_head == 0 ? AECM_MAX_DELAY - 1 : old_head - 1;
@@ -537,7 +581,7 @@ __device__ __forceinline__ void process_block(const Ctx &c, int in_rd, int clean
                         sh_num = 32 - (z_num + z_far);
                         upd = err > 0 ? (err >> sh_num) * (int)far : -((-err >> sh_num) * (int)far);
                     }
-                    upd = upd / (i + 1);  // :904
+                    upd = div_by_bin(upd, i + 1);  // :904 WebRtcSpl_DivW32W16(tmp32no2, i + 1)
                     const int sh2 = sh_num + sh_chfar - xq - mu - ((30 - z_far) << 1);
                     if (norm_w32(upd) < sh2) upd = 0x7fffffff;  // :908-912
                     else upd = shift_s32(upd, sh2);
@@ -1135,27 +1179,28 @@ __device__ __forceinline__ int api_process(const Ctx &c, bool live, const int16_
 
 // ---- 1-D bulk async copies (TMA unit) between the HBM record and the warp's shared-memory copy ----
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void bulk_load_record(void *dst_smem, const void *src_gmem, uint32_t bytes, uint64_t *bar, int lane) {
+// Issues the two bulk loads of the record (lane 0) and waits for part A; part B is waited for where it is first used.
+__device__ __forceinline__ void bulk_load_record(AecmInstanceState *dst_smem, const AecmInstanceState *src_gmem, uint32_t bytes,
+                                                 uint64_t *bar_a, uint64_t *bar_b, int lane) {
     if (lane == 0) {
-        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(bar)));
+        const uint32_t a = smem_u32(bar_a), b = smem_u32(bar_b);
+        const uint32_t bytes_b = bytes - AECM_STATE_PART_A;
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(a));
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(b));
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(a), "r"((uint32_t)AECM_STATE_PART_A) : "memory");
         asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
                          smem_u32(dst_smem)),
-                     "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+                     "l"(src_gmem), "r"((uint32_t)AECM_STATE_PART_A), "r"(a)
+                     : "memory");
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(b), "r"(bytes_b) : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                         smem_u32(reinterpret_cast<const char *>(dst_smem) + AECM_STATE_PART_A)),
+                     "l"(reinterpret_cast<const char *>(src_gmem) + AECM_STATE_PART_A), "r"(bytes_b), "r"(b)
                      : "memory");
     }
     __syncwarp();
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "WAIT_RECORD:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], 0;\n"
-        "@p bra DONE_RECORD;\n"
-        "bra WAIT_RECORD;\n"
-        "DONE_RECORD:\n"
-        "}\n" ::"r"(smem_u32(bar))
-        : "memory");
+    mbar_wait(bar_a);
 }
 __device__ __forceinline__ void bulk_store_record(void *dst_gmem, const void *src_smem, uint32_t bytes, int lane) {
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> visible to the async proxy
@@ -1184,7 +1229,10 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, kCtasPerSm) aecm_call_kerne
     const bool use_clean = a.near_clean != nullptr;
     const uint32_t rec_bytes = use_clean ? AECM_STATE_BYTES : AECM_STATE_BYTES_NOCLEAN;
     AecmInstanceState *g_state = planes.state + inst;
-    if (live) bulk_load_record(st, g_state, rec_bytes, &sc->mbar, lane);
+    if (live) {
+        bulk_load_record(st, g_state, rec_bytes, &sc->mbar_a, &sc->mbar_b, lane);
+        if (use_clean) mbar_wait(&sc->mbar_b);  // the clean-path tail is needed from the first frame on
+    }
 
     Ctx c;
     c.st = st;
@@ -1209,6 +1257,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, kCtasPerSm) aecm_call_kerne
         }
     }
     if (!live) return;
+    mbar_wait(&sc->mbar_b);  // (a start-up call never touched part B: make sure it has landed before it is stored back)
     bulk_store_record(g_state, st, rec_bytes, lane);
     if (a.status && lane == 0) a.status[row] = status;
 }

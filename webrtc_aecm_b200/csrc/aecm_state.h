@@ -71,19 +71,19 @@ typedef struct {
 } AecmScalars;
 
 typedef struct {
-    /* 65-bin adaptive state (padded so every array starts 16-byte aligned) */
-    int32_t ch_adapt32[68];
-    int32_t echo_filt[68];
-    int32_t noise_est[68];
-    int16_t ch_stored[72];
-    int16_t ch_adapt16[72];
-    int16_t near_filt[72];
-    uint8_t noise_low_ctr[80];
-    uint8_t noise_high_ctr[80];
-    /* time domain: previous block halves and the overlap-add tail */
+    /* ---- part A: what a call needs first (scalars, FIFOs, previous block halves); loaded by the first bulk copy */
+    AecmScalars s;
+    /* L3: last far frames for replay on underrun */
+    int16_t farend_old[2][AECM_FRAME_LEN];
+    /* L2 frame->block FIFOs */
+    int16_t frm_far[AECM_FRM_RING];
+    int16_t frm_near[AECM_FRM_RING];
+    int16_t frm_out[AECM_FRM_RING];
+    /* time domain: previous block halves */
     int16_t x_old[64];
     int16_t d_noisy_old[64];
-    int16_t out_ola[64];
+    /* ---- part B: needed only after the analysis FFTs; its bulk copy is waited for later ---- */
+    int16_t out_ola[64];             /* overlap-add tail */
     /* delay estimator: band thresholds (bands 12..43), binary far history ring, smoothed bit counts */
     int32_t thr_far[32];
     int32_t thr_near[32];
@@ -93,18 +93,22 @@ typedef struct {
     int16_t near_log[AECM_LOG_RING];
     int16_t echo_adapt_log[AECM_LOG_RING];
     int16_t echo_stored_log[AECM_LOG_RING];
-    /* L2 frame->block FIFOs */
-    int16_t frm_far[AECM_FRM_RING];
-    int16_t frm_near[AECM_FRM_RING];
-    int16_t frm_out[AECM_FRM_RING];
-    /* L3: last far frames for replay on underrun */
-    int16_t farend_old[2][AECM_FRAME_LEN];
-    AecmScalars s;
-    /* clean-path extension: only moved when a clean plane is supplied */
+    /* 65-bin adaptive state (padded so every array starts 16-byte aligned) */
+    int32_t ch_adapt32[68];
+    int32_t echo_filt[68];
+    int32_t noise_est[68];
+    int16_t ch_stored[72];
+    int16_t ch_adapt16[72];
+    int16_t near_filt[72];
+    uint8_t noise_low_ctr[80];
+    uint8_t noise_high_ctr[80];
+    /* ---- clean-path extension: only moved when a clean plane is supplied ---- */
     int16_t d_clean_old[64];
     int16_t frm_clean[AECM_FRM_RING];
 } AecmInstanceState;
 
+/* bytes of part A (multiple of 16) */
+#define AECM_STATE_PART_A ((int)(sizeof(AecmScalars) + 2 * AECM_FRAME_LEN * 2 + 3 * AECM_FRM_RING * 2 + 2 * 64 * 2))
 #define AECM_STATE_BYTES ((int)sizeof(AecmInstanceState))
 /* bytes a warp has to move when no clean plane is in use */
 #define AECM_STATE_BYTES_NOCLEAN ((int)(sizeof(AecmInstanceState) - 64 * 2 - AECM_FRM_RING * 2))
