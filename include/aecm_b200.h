@@ -76,7 +76,8 @@ int32_t AecmB200_ProcessStream(AecmB200Batch *batch, const AecmB200StreamArgs *h
 /* The same call split in two for double buffering: Submit enqueues H2D copies, the kernel and D2H copies for one of
  * two slots (0 or 1) and returns at once; Wait blocks until that slot's results (out planes, status) are in host
  * memory.  Kernels execute in submission order; the copies of one slot overlap the kernel of the other.  The host
- * planes (pinned for real overlap) and the status array must stay valid until Wait. */
+ * planes (pinned for real overlap) and the status array must stay valid until Wait.  Tip: if the dense near plane
+ * starts exactly where the dense far plane ends, both cross PCIe in one transfer. */
 int32_t AecmB200_SubmitStream(AecmB200Batch *batch, const AecmB200StreamArgs *hostArgs, int32_t slot);
 int32_t AecmB200_WaitStream(AecmB200Batch *batch, int32_t slot);
 /* Device-memory planes on the batch's GPU: enqueues on the batch stream and returns immediately. */
@@ -113,6 +114,10 @@ void AecmB200_HostFree(void *p);
 size_t AecmB200_StateBytes(void);
 int32_t AecmB200_ReadState(AecmB200Batch *batch, int32_t instance, void *dst, size_t bytes);
 int64_t AecmB200_KernelLaunchCount(void);
+/* Diagnostics: runs the device's floor-sqrt (the magnitude step, signal_processing_library.cc:76-105) over the
+ * arguments [first, first + count) on the current device and returns how many differ from the reference's
+ * bit-by-bit construction (0 expected; negative = CUDA error). */
+int64_t AecmB200_SelfTestSqrtFloor(uint32_t first, uint32_t count);
 int32_t AecmB200_DeviceCount(void);
 
 #ifdef __cplusplus

@@ -193,9 +193,21 @@ def test_ragged_ranges_and_partial_batches():
     b.close()
 
 
-def test_double_buffered_submit_wait_equals_synchronous():
+def test_device_floor_sqrt_is_exact_on_all_2_to_31_arguments():
+    """The magnitude step uses one hardware square-root estimate plus two integer corrections; swept exhaustively on
+    the device against the reference's bit-by-bit construction (signal_processing_library.cc:76-105)."""
+    from webrtc_aecm_b200 import api
+
+    L = api.lib()
+    assert L.AecmB200_SelfTestSqrtFloor(0, 1 << 30) == 0
+    assert L.AecmB200_SelfTestSqrtFloor(1 << 30, 1 << 30) == 0
+
+
+@pytest.mark.parametrize("adjacent", [False, True], ids=["separate_planes", "near_follows_far"])
+def test_double_buffered_submit_wait_equals_synchronous(adjacent):
     """AecmB200_SubmitStream / WaitStream with two slots (copies of call k+1 overlap the kernel of call k) must give
-    exactly the outputs of the synchronous call sequence."""
+    exactly the outputs of the synchronous call sequence.  With `adjacent` every call's near plane starts where its
+    far plane ends, which the library turns into a single host-to-device transfer."""
     import ctypes as C
 
     from webrtc_aecm_b200 import AecmBatch, api
@@ -206,7 +218,11 @@ def test_double_buffered_submit_wait_equals_synchronous():
     # [call][instance][samples] so every call's plane is dense
     hfar = np.ascontiguousarray(far.reshape(n, calls, spc).transpose(1, 0, 2))
     hnear = np.ascontiguousarray(near.reshape(n, calls, spc).transpose(1, 0, 2))
-    hout = np.zeros_like(hnear)
+    if adjacent:
+        hin = np.ascontiguousarray(np.stack([hfar, hnear], axis=1))  # [call][far|near][instance][samples]
+        hfar, hnear = hin[:, 0], hin[:, 1]
+        assert hnear[3].ctypes.data == hfar[3].ctypes.data + hfar[3].nbytes
+    hout = np.zeros_like(near).reshape(calls, n, spc)
     status = [np.zeros(n, dtype=np.int32) for _ in range(2)]
     b = AecmBatch(n, 0)
     assert b.init(fs) == 0

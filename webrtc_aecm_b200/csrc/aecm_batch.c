@@ -129,7 +129,7 @@ void AecmB200_Free(AecmB200Batch *b) {
     for (int i = 0; i < AECM_SLOTS; i++) {
         Slot *sl = &b->slot[i];
         if (sl->copy) cudaStreamSynchronize(sl->copy);
-        cudaFree(sl->d_far); cudaFree(sl->d_near); cudaFree(sl->d_clean); cudaFree(sl->d_out);
+        cudaFree(sl->d_far); cudaFree(sl->d_clean); cudaFree(sl->d_out); /* d_near lives inside d_far's allocation */
         cudaFree(sl->d_ms); cudaFree(sl->d_mask); cudaFree(sl->d_status);
         cudaFreeHost(sl->h_status);
         if (sl->copy) cudaStreamDestroy(sl->copy);
@@ -179,6 +179,7 @@ void AecmB200_HostFree(void *p) {
 
 size_t AecmB200_StateBytes(void) { return sizeof(AecmInstanceState); }
 int64_t AecmB200_KernelLaunchCount(void) { return aecm_cuda_kernel_launch_count(); }
+int64_t AecmB200_SelfTestSqrtFloor(uint32_t first, uint32_t count) { return aecm_cuda_selftest_sqrt(first, count); }
 
 /* Called before enqueuing anything on the main stream: order it after the kernels of earlier submissions and
  * remember that later submissions have to follow it. */
@@ -318,13 +319,15 @@ int32_t AecmB200_ProcessStreamDevice(AecmB200Batch *b, const AecmB200StreamArgs 
     return 0;
 }
 
+/* The far and near staging planes are carved out of ONE allocation, far first, so that a caller who keeps its own
+ * far and near planes adjacent in host memory gets them across PCIe in a single DMA (each transfer costs a fixed
+ * ~10 us on top of its bytes). */
 static int grow_planes(AecmB200Batch *b, Slot *sl, size_t samples, int need_clean) {
     if (samples > sl->plane_samples) {
-        cudaFree(sl->d_far); cudaFree(sl->d_near); cudaFree(sl->d_clean); cudaFree(sl->d_out);
+        cudaFree(sl->d_far); cudaFree(sl->d_clean); cudaFree(sl->d_out);
         sl->d_far = sl->d_near = sl->d_clean = sl->d_out = NULL;
         sl->plane_samples = 0;
-        CU(b, cudaMalloc((void **)&sl->d_far, samples * sizeof(int16_t)));
-        CU(b, cudaMalloc((void **)&sl->d_near, samples * sizeof(int16_t)));
+        CU(b, cudaMalloc((void **)&sl->d_far, 2 * samples * sizeof(int16_t)));
         CU(b, cudaMalloc((void **)&sl->d_out, samples * sizeof(int16_t)));
         sl->plane_samples = samples;
     }
@@ -347,6 +350,7 @@ int32_t AecmB200_SubmitStream(AecmB200Batch *b, const AecmB200StreamArgs *h, int
     AecmCallArgs k;
     Slot *sl;
     int32_t rc;
+    int adjacent;
     if (!b) return -1;
     if (slot < 0 || slot >= AECM_SLOTS) return AECM_BAD_PARAMETER_ERROR;
     rc = validate_stream_args(b, h);
@@ -373,12 +377,19 @@ int32_t AecmB200_SubmitStream(AecmB200Batch *b, const AecmB200StreamArgs *h, int
     }
     if (b->trace) CU(b, cudaEventRecord(sl->t[0], sl->copy));
     memset(&k, 0, sizeof(k));
-    if (h->farend) {
+    sl->d_near = sl->d_far + rows * width; /* right behind the far plane of this call */
+    /* dense far plane immediately followed by the dense near plane: one DMA for both */
+    adjacent = h->farend && h->nearendNoisy && pitch_src == pitch_dst && h->nearendNoisy == h->farend + rows * width;
+    if (adjacent) {
+        CU(b, cudaMemcpyAsync(sl->d_far, h->farend, 2 * rows * pitch_dst, cudaMemcpyHostToDevice, sl->copy));
+        k.far = sl->d_far;
+    } else if (h->farend) {
         CU(b, copy_plane(sl->d_far, pitch_dst, h->farend, pitch_src, pitch_dst, rows, cudaMemcpyHostToDevice, sl->copy));
         k.far = sl->d_far;
     }
     if (h->nearendNoisy) {
-        CU(b, copy_plane(sl->d_near, pitch_dst, h->nearendNoisy, pitch_src, pitch_dst, rows, cudaMemcpyHostToDevice, sl->copy));
+        if (!adjacent)
+            CU(b, copy_plane(sl->d_near, pitch_dst, h->nearendNoisy, pitch_src, pitch_dst, rows, cudaMemcpyHostToDevice, sl->copy));
         k.near_noisy = sl->d_near;
         k.out = sl->d_out;
         if (h->nearendClean) {

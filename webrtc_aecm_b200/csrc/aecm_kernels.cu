@@ -170,9 +170,14 @@ __device__ __forceinline__ int shift_s32(int x, int c) {
 }
 __device__ __forceinline__ uint32_t shift_u32(uint32_t x, int c) { return c >= 0 ? x << (c & 31) : x >> ((-c) & 31); }
 
-// signal_processing_library.cc:84-105 is floor(sqrt(v)) for v in [0, 2^31)
+// signal_processing_library.cc:84-105 is floor(sqrt(v)) for v in [0, 2^31).  One MUFU.SQRT
+// (relative error <= 2^-23: the estimate is within 0.01 of the root on this range) instead of the IEEE sqrtf sequence
+// with its slow-path call; the two integer corrections make the result exact for ANY estimate within +-1 of the root.
+// aecm_sqrt_selftest_kernel below sweeps all 2^31 arguments on the device (tests/test_gpu_parity.py).
 __device__ __forceinline__ int sqrt_floor(int v) {
-    uint32_t r = (uint32_t)__float2int_rz(sqrtf((float)v));
+    float f;
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(f) : "f"(__uint2float_rn((uint32_t)v)));
+    uint32_t r = (uint32_t)__float2int_rz(f);
     if (r * r > (uint32_t)v) r--;
     if ((r + 1) * (r + 1) <= (uint32_t)v) r++;
     return (int)r;
@@ -1202,6 +1207,7 @@ __device__ __forceinline__ void bulk_load_record(AecmInstanceState *dst_smem, co
     __syncwarp();
     mbar_wait(bar_a);
 }
+__device__ __forceinline__ void prefetch_line(const void *p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
 __device__ __forceinline__ void bulk_store_record(void *dst_gmem, const void *src_smem, uint32_t bytes, int lane) {
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> visible to the async proxy
     __syncwarp();
@@ -1229,8 +1235,27 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, kCtasPerSm) aecm_call_kerne
     const bool use_clean = a.near_clean != nullptr;
     const uint32_t rec_bytes = use_clean ? AECM_STATE_BYTES : AECM_STATE_BYTES_NOCLEAN;
     AecmInstanceState *g_state = planes.state + inst;
+    const int64_t off = (int64_t)row * a.row_stride;
+    int16_t *const far_ring = planes.far_ring + (size_t)inst * AECM_FAR_RING;
     if (live) {
+        // The audio rows of the first call are needed right after the record: start them on their way from HBM now,
+        // one 128-byte line per lane, so that their latency overlaps the record copy instead of following it.
+        const int row_bytes = a.samples_per_call * (int)sizeof(int16_t);
+        const int at = min(lane * 128, row_bytes - 1);  // lane 0.. cover the row, the last one its final byte
+        if (lane * 128 < row_bytes + 128) {
+            if (a.far) prefetch_line(reinterpret_cast<const char *>(a.far + off) + at);
+            if (a.near_noisy) prefetch_line(reinterpret_cast<const char *>(a.near_noisy + off) + at);
+            if (use_clean) prefetch_line(reinterpret_cast<const char *>(a.near_clean + off) + at);
+        }
         bulk_load_record(st, g_state, rec_bytes, &sc->mbar_a, &sc->mbar_b, lane);
+        // ... and the stretch of the far-end jitter ring this call will read back (echo_control_mobile.cc:369-380:
+        // up to 160 samples from the read cursor, which EstBufDelay may first move by one frame either way)
+        if (lane < 6) {
+            int pos = st->s.far_rd - AECM_FRAME_LEN + lane * 64;
+            pos += pos < 0 ? AECM_FAR_RING : 0;
+            pos -= pos >= AECM_FAR_RING ? AECM_FAR_RING : 0;
+            prefetch_line(far_ring + pos);
+        }
         if (use_clean) mbar_wait(&sc->mbar_b);  // the clean-path tail is needed from the first frame on
     }
 
@@ -1238,14 +1263,18 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, kCtasPerSm) aecm_call_kerne
     c.st = st;
     c.sc = sc;
     c.far_hist = planes.far_hist + (size_t)inst * AECM_MAX_DELAY * AECM_HIST_ROW;
-    c.far_ring = planes.far_ring + (size_t)inst * AECM_FAR_RING;
+    c.far_ring = far_ring;
     c.lane = lane;
 
-    const int64_t off = (int64_t)row * a.row_stride;
     const int ms = (a.ms && live) ? (int)a.ms[row] : a.ms_uniform;
     int status = 0;
     for (int call = 0; call < a.n_calls; call++) {
         const int64_t o = off + (int64_t)call * a.samples_per_call;
+        if (live && call + 1 < a.n_calls && lane * 128 < a.samples_per_call * 2) {  // the next call's audio, one line per lane
+            const int64_t nx = (o + a.samples_per_call) * (int64_t)sizeof(int16_t) + lane * 128;
+            if (a.far) prefetch_line(reinterpret_cast<const char *>(a.far) + nx);
+            if (a.near_noisy) prefetch_line(reinterpret_cast<const char *>(a.near_noisy) + nx);
+        }
         if (live && a.far && (!a.far_mask || a.far_mask[(size_t)call * a.mask_stride + row])) {
             const int r = api_buffer_farend(c, a.far + o, a.samples_per_call);
             if (status == 0) status = r;
@@ -1364,6 +1393,25 @@ int g_launches = 0;
 
 }  // namespace
 
+// Exhaustive check of sqrt_floor against the reference's bit-by-bit construction (signal_processing_library.cc:84-105:
+// sixteen trial-and-subtract steps from bit 15 down).  Counts the arguments in [first, first + count) that disagree.
+__global__ void aecm_sqrt_selftest_kernel(uint32_t first, uint32_t count, unsigned long long *bad) {
+    unsigned long long mine = 0;
+    for (uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; k < count; k += (uint64_t)gridDim.x * blockDim.x) {
+        const uint32_t v = first + (uint32_t)k;
+        uint32_t root = 0, rem = v;
+        for (int bit = 15; bit >= 0; bit--) {
+            const uint32_t trial = ((root << 1) + (1u << bit)) << bit;  // (root + 2^bit)^2 - root^2
+            if (rem >= trial) {
+                rem -= trial;
+                root |= 1u << bit;
+            }
+        }
+        mine += (uint32_t)sqrt_floor((int)v) != root;
+    }
+    if (mine) atomicAdd(bad, mine);
+}
+
 extern "C" {
 
 int aecm_cuda_kernel_launch_count(void) { return g_launches; }
@@ -1403,19 +1451,33 @@ int aecm_cuda_launch_init_echo_path(const AecmBatchPlanes *p, int first, int cou
 
 int aecm_cuda_launch_call(const AecmBatchPlanes *p, const AecmCallArgs *a, void *stream) {
     if (a->count <= 0 || a->n_calls <= 0) return 0;
-    static bool attr_set = false;
+    static bool attr_set[64] = {};  // function attributes are per device
     const size_t smem = (size_t)kWarpsPerCta * (sizeof(AecmInstanceState) + sizeof(WarpScratch));
-    if (!attr_set) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return (int)cudaErrorInvalidDevice;
+    if (!attr_set[dev]) {
         cudaError_t e = cudaFuncSetAttribute(aecm_call_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return (int)e;
         e = cudaFuncSetAttribute(aecm_call_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
         if (e != cudaSuccess) return (int)e;
-        attr_set = true;
+        attr_set[dev] = true;
     }
     const int blocks = (a->count + kWarpsPerCta - 1) / kWarpsPerCta;
     aecm_call_kernel<<<blocks, kWarpsPerCta * 32, smem, static_cast<cudaStream_t>(stream)>>>(*p, *a);
     g_launches++;
     return (int)cudaGetLastError();
+}
+
+// diagnostics: number of arguments in [first, first + count) for which the device sqrt_floor differs from the
+// reference construction; negative = CUDA error
+long long aecm_cuda_selftest_sqrt(uint32_t first, uint32_t count) {
+    unsigned long long *d_bad = nullptr, bad = 0;
+    if (cudaMalloc(&d_bad, sizeof(bad)) != cudaSuccess) return -1;
+    cudaMemset(d_bad, 0, sizeof(bad));
+    aecm_sqrt_selftest_kernel<<<148 * 8, 256>>>(first, count, d_bad);
+    cudaError_t e = cudaMemcpy(&bad, d_bad, sizeof(bad), cudaMemcpyDeviceToHost);
+    cudaFree(d_bad);
+    return e == cudaSuccess ? (long long)bad : -(long long)e;
 }
 
 }  // extern "C"
