@@ -69,17 +69,22 @@ typedef struct {
     int16_t msUniform;            /* used when msInSndCardBuf is NULL */
     const uint8_t *farendMask;    /* optional [nCalls][count] */
     int32_t *status;              /* optional [count] */
+    const int32_t *instanceIndex; /* optional [count]: plane row r is instance instanceIndex[r] instead of first + r;
+                                     the indices must be distinct (one warp per row, no locking); `first` is ignored */
 } AecmB200StreamArgs;
 
 /* Host-memory planes: copies in, runs, copies out and waits (pinned planes avoid the staging copy). */
 int32_t AecmB200_ProcessStream(AecmB200Batch *batch, const AecmB200StreamArgs *hostArgs);
-/* The same call split in two for double buffering: Submit enqueues H2D copies, the kernel and D2H copies for one of
- * two slots (0 or 1) and returns at once; Wait blocks until that slot's results (out planes, status) are in host
- * memory.  Kernels execute in submission order; the copies of one slot overlap the kernel of the other.  The host
- * planes (pinned for real overlap) and the status array must stay valid until Wait.  Tip: if the dense near plane
- * starts exactly where the dense far plane ends, both cross PCIe in one transfer. */
+/* The same call split in two for pipelining: Submit enqueues the H2D copies, the kernel and the D2H copies on one of
+ * AecmB200_NumStreamSlots() slots (0 .. n-1) and returns at once; Wait blocks until that slot's results (out planes,
+ * status) are in host memory, after which the slot may be submitted to again.  Kernels execute in submission order;
+ * the copies of one slot overlap the kernels and copies of the others.  A call occupies its slot for H2D + kernel +
+ * D2H, so keeping the PCIe link busy takes three or four calls in flight (round-robin over the slots, waiting for
+ * the oldest).  The host planes (pinned for real overlap) and the status array must stay valid until Wait.  Tip: if
+ * the dense near plane starts exactly where the dense far plane ends, both cross PCIe in one transfer. */
 int32_t AecmB200_SubmitStream(AecmB200Batch *batch, const AecmB200StreamArgs *hostArgs, int32_t slot);
 int32_t AecmB200_WaitStream(AecmB200Batch *batch, int32_t slot);
+int32_t AecmB200_NumStreamSlots(void);
 /* Device-memory planes on the batch's GPU: enqueues on the batch stream and returns immediately. */
 int32_t AecmB200_ProcessStreamDevice(AecmB200Batch *batch, const AecmB200StreamArgs *deviceArgs);
 
@@ -114,6 +119,9 @@ void AecmB200_HostFree(void *p);
 size_t AecmB200_StateBytes(void);
 int32_t AecmB200_ReadState(AecmB200Batch *batch, int32_t instance, void *dst, size_t bytes);
 int64_t AecmB200_KernelLaunchCount(void);
+/* Diagnostics of the scalar API's call combiner (echo_control_mobile.c): rounds run and BufferFarend/Process requests
+ * served so far by the pool the instance `aecmInst` (a WebRtcAecm_Create handle) lives in. */
+void AecmB200_ScalarApiStats(void *aecmInst, int64_t *rounds, int64_t *requests);
 /* Diagnostics: runs the device's floor-sqrt (the magnitude step, signal_processing_library.cc:76-105) over the
  * arguments [first, first + count) on the current device and returns how many differ from the reference's
  * bit-by-bit construction (0 expected; negative = CUDA error). */

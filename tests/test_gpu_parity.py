@@ -203,11 +203,13 @@ def test_device_floor_sqrt_is_exact_on_all_2_to_31_arguments():
     assert L.AecmB200_SelfTestSqrtFloor(1 << 30, 1 << 30) == 0
 
 
-@pytest.mark.parametrize("adjacent", [False, True], ids=["separate_planes", "near_follows_far"])
-def test_double_buffered_submit_wait_equals_synchronous(adjacent):
-    """AecmB200_SubmitStream / WaitStream with two slots (copies of call k+1 overlap the kernel of call k) must give
-    exactly the outputs of the synchronous call sequence.  With `adjacent` every call's near plane starts where its
-    far plane ends, which the library turns into a single host-to-device transfer."""
+@pytest.mark.parametrize("adjacent,all_slots", [(False, False), (True, False), (True, True)],
+                         ids=["separate_planes", "near_follows_far", "all_slots_in_flight"])
+def test_pipelined_submit_wait_equals_synchronous(adjacent, all_slots):
+    """AecmB200_SubmitStream / WaitStream (copies of later calls overlap the kernels of earlier ones) must give exactly
+    the outputs of the synchronous call sequence, with two calls in flight or with every slot in use.  With `adjacent`
+    every call's near plane starts where its far plane ends, which the library turns into a single host-to-device
+    transfer."""
     import ctypes as C
 
     from webrtc_aecm_b200 import AecmBatch, api
@@ -223,24 +225,69 @@ def test_double_buffered_submit_wait_equals_synchronous(adjacent):
         hfar, hnear = hin[:, 0], hin[:, 1]
         assert hnear[3].ctypes.data == hfar[3].ctypes.data + hfar[3].nbytes
     hout = np.zeros_like(near).reshape(calls, n, spc)
-    status = [np.zeros(n, dtype=np.int32) for _ in range(2)]
+    L = api.lib()
+    n_slots = L.AecmB200_NumStreamSlots()
+    assert n_slots >= 2
+    S = n_slots if all_slots else 2
+    status = [np.zeros(n, dtype=np.int32) for _ in range(S)]
     b = AecmBatch(n, 0)
     assert b.init(fs) == 0
-    L = api.lib()
 
     def submit(k):
         a = api.StreamArgs(hfar[k].ctypes.data, hnear[k].ctypes.data, None, hout[k].ctypes.data, spc, 0, n, spc, 1, None, 40,
-                           None, status[k % 2].ctypes.data)
-        assert L.AecmB200_SubmitStream(b._h, C.byref(a), k % 2) == 0
+                           None, status[k % S].ctypes.data)
+        assert L.AecmB200_SubmitStream(b._h, C.byref(a), k % S) == 0
+
+    def wait(k):
+        assert L.AecmB200_WaitStream(b._h, k % S) == 0 and not status[k % S].any()
 
     submit(0)
-    assert L.AecmB200_SubmitStream(b._h, None, 0) == 12003  # NULL args
+    assert L.AecmB200_SubmitStream(b._h, None, 1) == 12003  # NULL args
+    a_busy = api.StreamArgs(hfar[0].ctypes.data, hnear[0].ctypes.data, None, hout[0].ctypes.data, spc, 0, n, spc, 1, None, 40, None, None)
+    assert L.AecmB200_SubmitStream(b._h, C.byref(a_busy), 0) == 12004  # slot 0 is still in flight
+    assert L.AecmB200_SubmitStream(b._h, C.byref(a_busy), n_slots) == 12004  # no such slot
     for k in range(1, calls):
         submit(k)
-        assert L.AecmB200_WaitStream(b._h, (k - 1) % 2) == 0 and not status[(k - 1) % 2].any()
-    assert L.AecmB200_WaitStream(b._h, (calls - 1) % 2) == 0
+        if k - (S - 1) >= 0:
+            wait(k - (S - 1))
+    for k in range(calls - (S - 1), calls):
+        wait(k)
     got = hout.transpose(1, 0, 2).reshape(n, calls * spc)
     np.testing.assert_array_equal(got, want)
+    b.close()
+
+
+def test_instance_index_scatters_rows_over_the_batch():
+    """AecmB200StreamArgs.instanceIndex: plane row r works on instance instanceIndex[r].  A permuted subset of a batch,
+    driven through host planes, must equal the oracle per stream while the untouched instances stay untouched."""
+    import ctypes as C
+
+    from webrtc_aecm_b200 import AecmBatch, api
+
+    fs, spc, n, calls, total = 16000, 160, 40, 60, 100
+    far, near = synth_streams(n, calls * spc, fs, seed=1234, delay_ms=np.arange(n) * 2)
+    want, _, _ = ol.run_streams(far, near, fs=fs, impl="oracle")
+    rng = np.random.default_rng(3)
+    index = np.ascontiguousarray(rng.permutation(total)[:n].astype(np.int32))
+    b = AecmBatch(total, 0)
+    assert b.init(fs) == 0
+    L = api.lib()
+    out = np.zeros_like(near)
+    status = np.ones(n, dtype=np.int32)
+    for k0 in range(0, calls, 7):  # several launches, 7 (then fewer) fused calls each
+        k1 = min(calls, k0 + 7)
+        a = api.StreamArgs(far[:, k0 * spc:].ctypes.data, near[:, k0 * spc:].ctypes.data, None, out[:, k0 * spc:].ctypes.data,
+                           calls * spc, 0, n, spc, k1 - k0, None, 40, None, status.ctypes.data, index.ctypes.data)
+        assert L.AecmB200_ProcessStream(b._h, C.byref(a)) == 0 and not status.any()
+    np.testing.assert_array_equal(out, want)
+    touched = set(index.tolist())
+    for inst in range(total):
+        tot = b.read_state(inst).s.tot_count
+        assert (tot > 0) == (inst in touched), inst
+    bad = index.copy()
+    bad[5] = total  # out of range
+    a = api.StreamArgs(far.ctypes.data, near.ctypes.data, None, out.ctypes.data, calls * spc, 0, n, spc, 1, None, 40, None, None, bad.ctypes.data)
+    assert L.AecmB200_ProcessStream(b._h, C.byref(a)) == 12004
     b.close()
 
 

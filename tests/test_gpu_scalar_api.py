@@ -107,3 +107,59 @@ def test_echo_path_round_trip_matches_oracle():
     assert lib.oracle_aecm_get_echo_path(o.h, wantp.ctypes.data_as(C.c_void_p), 130) == 0
     np.testing.assert_array_equal(got, wantp)
     L.WebRtcAecm_Free(h)
+
+
+def test_scalar_api_from_many_threads_is_combined_and_bit_exact():
+    """Different instances driven from different threads at the same time, as the reference allows (SURVEY 8b
+    threading).  Calls that arrive while a launch is in flight are combined into the next launch; every stream must
+    still equal the oracle, and the combiner must have served the requests in fewer rounds than requests."""
+    import threading
+
+    from webrtc_aecm_b200 import api
+
+    L = api.scalar_api()
+    fs, spc, calls, T = 16000, 160, 120, 24
+    far, near = synth_streams(T, calls * spc, fs, seed=515, delay_ms=np.arange(T) * 3)
+    clean = np.ascontiguousarray(near[:, ::-1] // 3)
+    use_clean = np.arange(T) % 4 == 3  # a few instances take the clean path (a separate launch group)
+    want = np.zeros_like(near)
+    for sel, cl in ((~use_clean, None), (use_clean, clean[use_clean])):
+        want[sel], _, _ = ol.run_streams(far[sel], near[sel], fs=fs, impl="oracle", echo_mode=2, clean=cl, ms=np.arange(T)[sel] * 5)
+    got = np.zeros_like(near)
+    hs = [L.WebRtcAecm_Create() for _ in range(T)]
+    errors = []
+    start = threading.Barrier(T)
+
+    def worker(i):
+        try:
+            h = hs[i]
+            assert L.WebRtcAecm_Init(h, fs) == 0
+            assert L.WebRtcAecm_set_config(h, api.AecmConfig(1, 2)) == 0
+            start.wait()
+            for c in range(calls):
+                f = np.ascontiguousarray(far[i, c * spc:(c + 1) * spc])
+                n = np.ascontiguousarray(near[i, c * spc:(c + 1) * spc])
+                cl = np.ascontiguousarray(clean[i, c * spc:(c + 1) * spc]) if use_clean[i] else None
+                out = got[i, c * spc:(c + 1) * spc]
+                assert L.WebRtcAecm_BufferFarend(h, P(f), spc) == 0
+                assert L.WebRtcAecm_Process(h, P(n), P(cl) if cl is not None else None, P(out), spc, i * 5) == 0
+        except BaseException as e:  # noqa: BLE001 - reported by the main thread
+            errors.append((i, repr(e)))
+
+    r0, q0 = C.c_int64(0), C.c_int64(0)
+    L.AecmB200_ScalarApiStats(hs[0], C.byref(r0), C.byref(q0))
+    threads = [threading.Thread(target=worker, args=(i,)) for i in range(T)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    assert not errors, errors
+    np.testing.assert_array_equal(got, want)
+    r1, q1 = C.c_int64(0), C.c_int64(0)
+    L.AecmB200_ScalarApiStats(hs[0], C.byref(r1), C.byref(q1))
+    requests, rounds = q1.value - q0.value, r1.value - r0.value
+    assert requests == 2 * T * calls
+    assert rounds < requests, (rounds, requests)  # some rounds carried more than one request
+    print(f"combiner: {requests} requests in {rounds} rounds ({requests / rounds:.1f} per round)")
+    for h in hs:
+        L.WebRtcAecm_Free(h)

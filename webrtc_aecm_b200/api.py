@@ -35,7 +35,7 @@ class StreamArgs(C.Structure):
     _fields_ = [("farend", C.c_void_p), ("nearendNoisy", C.c_void_p), ("nearendClean", C.c_void_p), ("out", C.c_void_p),
                 ("rowStride", C.c_int64), ("first", C.c_int32), ("count", C.c_int32), ("nrOfSamples", C.c_int32),
                 ("nCalls", C.c_int32), ("msInSndCardBuf", C.c_void_p), ("msUniform", C.c_int16),
-                ("farendMask", C.c_void_p), ("status", C.c_void_p)]
+                ("farendMask", C.c_void_p), ("status", C.c_void_p), ("instanceIndex", C.c_void_p)]
 
 
 class Scalars(C.Structure):
@@ -101,7 +101,8 @@ def lib():
             "AecmB200_Synchronize": (i32, [vp]), "AecmB200_CudaStream": (vp, [vp]),
             "AecmB200_AdoptCudaStream": (i32, [vp, vp]),
             "AecmB200_HostAlloc": (vp, [C.c_size_t]), "AecmB200_HostFree": (None, [vp]),
-            "AecmB200_SelfTestSqrtFloor": (C.c_int64, [C.c_uint32, C.c_uint32]),
+            "AecmB200_SelfTestSqrtFloor": (C.c_int64, [C.c_uint32, C.c_uint32]), "AecmB200_NumStreamSlots": (i32, []),
+            "AecmB200_ScalarApiStats": (None, [vp, C.POINTER(i64), C.POINTER(i64)]),
             "AecmB200_StateBytes": (C.c_size_t, []), "AecmB200_ReadState": (i32, [vp, i32, vp, C.c_size_t]),
             "AecmB200_KernelLaunchCount": (i64, []), "AecmB200_DeviceCount": (i32, []),
             # the reference's scalar API

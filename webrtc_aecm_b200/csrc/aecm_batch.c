@@ -12,7 +12,8 @@
 
 #include "aecm_state.h"
 
-#define AECM_SLOTS 2 /* in-flight host-plane submissions (double buffering) */
+#define AECM_SLOTS 4 /* in-flight host-plane submissions: H2D, kernel and D2H of different calls overlap (a call holds
+                        its slot for H2D + kernel + D2H, so keeping the H2D engine busy takes more than two) */
 
 /* One in-flight host-plane submission: device staging planes, a copy stream and the events that order
  * H2D -> kernel (on the batch's compute stream, so kernels stay in submission order) -> D2H. */
@@ -20,6 +21,7 @@ typedef struct {
     int16_t *d_far, *d_near, *d_clean, *d_out;
     size_t plane_samples;
     int16_t *d_ms;
+    int32_t *d_index;
     uint8_t *d_mask;
     size_t mask_bytes;
     int32_t *d_status, *h_status; /* h_status is pinned */
@@ -91,6 +93,7 @@ AecmB200Batch *AecmB200_Create(int32_t n, int32_t device) {
     for (int i = 0; i < AECM_SLOTS; i++) {
         Slot *sl = &b->slot[i];
         if (cudaMalloc((void **)&sl->d_ms, (size_t)n * sizeof(int16_t)) != cudaSuccess ||
+            cudaMalloc((void **)&sl->d_index, (size_t)n * sizeof(int32_t)) != cudaSuccess ||
             cudaMalloc((void **)&sl->d_status, (size_t)n * sizeof(int32_t)) != cudaSuccess ||
             cudaMallocHost((void **)&sl->h_status, (size_t)n * sizeof(int32_t)) != cudaSuccess ||
             cudaStreamCreateWithFlags(&sl->copy, cudaStreamNonBlocking) != cudaSuccess ||
@@ -130,7 +133,7 @@ void AecmB200_Free(AecmB200Batch *b) {
         Slot *sl = &b->slot[i];
         if (sl->copy) cudaStreamSynchronize(sl->copy);
         cudaFree(sl->d_far); cudaFree(sl->d_clean); cudaFree(sl->d_out); /* d_near lives inside d_far's allocation */
-        cudaFree(sl->d_ms); cudaFree(sl->d_mask); cudaFree(sl->d_status);
+        cudaFree(sl->d_ms); cudaFree(sl->d_index); cudaFree(sl->d_mask); cudaFree(sl->d_status);
         cudaFreeHost(sl->h_status);
         if (sl->copy) cudaStreamDestroy(sl->copy);
         if (sl->h2d_done) cudaEventDestroy(sl->h2d_done);
@@ -179,6 +182,7 @@ void AecmB200_HostFree(void *p) {
 
 size_t AecmB200_StateBytes(void) { return sizeof(AecmInstanceState); }
 int64_t AecmB200_KernelLaunchCount(void) { return aecm_cuda_kernel_launch_count(); }
+int32_t AecmB200_NumStreamSlots(void) { return AECM_SLOTS; }
 int64_t AecmB200_SelfTestSqrtFloor(uint32_t first, uint32_t count) { return aecm_cuda_selftest_sqrt(first, count); }
 
 /* Called before enqueuing anything on the main stream: order it after the kernels of earlier submissions and
@@ -282,7 +286,8 @@ static int32_t validate_stream_args(const AecmB200Batch *b, const AecmB200Stream
     if (!a->farend && !a->nearendNoisy) return AECM_NULL_POINTER_ERROR;
     if (a->nearendNoisy && !a->out) return AECM_NULL_POINTER_ERROR;            /* echo_control_mobile.cc:256-262 */
     if (a->nrOfSamples != 80 && a->nrOfSamples != 160) return AECM_BAD_PARAMETER_ERROR; /* :209, :268 */
-    if (a->nCalls < 1 || !range_ok(b, a->first, a->count)) return AECM_BAD_PARAMETER_ERROR;
+    if (a->nCalls < 1) return AECM_BAD_PARAMETER_ERROR;
+    if (a->instanceIndex ? (a->count < 0 || a->count > b->n) : !range_ok(b, a->first, a->count)) return AECM_BAD_PARAMETER_ERROR;
     if (a->rowStride < (int64_t)a->nCalls * a->nrOfSamples) return AECM_BAD_PARAMETER_ERROR;
     return 0;
 }
@@ -303,6 +308,7 @@ static void fill_call_args(AecmCallArgs *k, const AecmB200StreamArgs *a) {
     k->n_calls = a->nCalls;
     k->ms_uniform = a->msUniform;
     k->mask_stride = a->count;
+    k->index = a->instanceIndex;
 }
 
 int32_t AecmB200_ProcessStreamDevice(AecmB200Batch *b, const AecmB200StreamArgs *a) {
@@ -355,6 +361,11 @@ int32_t AecmB200_SubmitStream(AecmB200Batch *b, const AecmB200StreamArgs *h, int
     if (slot < 0 || slot >= AECM_SLOTS) return AECM_BAD_PARAMETER_ERROR;
     rc = validate_stream_args(b, h);
     if (rc) return rc;
+    if (h->instanceIndex) { /* a host array here (a device array in AecmB200_ProcessStreamDevice, checked by the kernel) */
+        int32_t r;
+        for (r = 0; r < h->count; r++)
+            if (h->instanceIndex[r] < 0 || h->instanceIndex[r] >= b->n) return AECM_BAD_PARAMETER_ERROR;
+    }
     sl = &b->slot[slot];
     if (sl->busy) return AECM_BAD_PARAMETER_ERROR; /* the previous submission on this slot was not waited for */
     CU(b, cudaSetDevice(b->device));
@@ -400,6 +411,10 @@ int32_t AecmB200_SubmitStream(AecmB200Batch *b, const AecmB200StreamArgs *h, int
     if (h->msInSndCardBuf) {
         CU(b, cudaMemcpyAsync(sl->d_ms, h->msInSndCardBuf, rows * sizeof(int16_t), cudaMemcpyHostToDevice, sl->copy));
         k.ms = sl->d_ms;
+    }
+    if (h->instanceIndex) {
+        CU(b, cudaMemcpyAsync(sl->d_index, h->instanceIndex, rows * sizeof(int32_t), cudaMemcpyHostToDevice, sl->copy));
+        k.index = sl->d_index;
     }
     if (h->farendMask) {
         const size_t mb = rows * (size_t)h->nCalls;
@@ -591,7 +606,7 @@ int32_t AecmB200_GroupProcessStream(AecmB200Group *g, const AecmB200StreamArgs *
     if (!g) return -1;
     if (!h) return AECM_NULL_POINTER_ERROR;
     if (h->first < 0 || h->count < 0 || (int64_t)h->first + h->count > g->n) return AECM_BAD_PARAMETER_ERROR;
-    if (h->farendMask) return AECM_UNSUPPORTED_FUNCTION_ERROR; /* the mask is laid out per call over the whole range */
+    if (h->farendMask || h->instanceIndex) return AECM_UNSUPPORTED_FUNCTION_ERROR; /* both are laid out over the whole range */
     for (i = 0; i < g->n_shards; i++) { /* submit the shard-local slice of the range to every device ... */
         const int32_t lo = h->first > g->first[i] ? h->first : g->first[i];
         const int32_t hi = h->first + h->count < g->first[i + 1] ? h->first + h->count : g->first[i + 1];

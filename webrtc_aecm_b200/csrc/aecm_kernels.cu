@@ -1231,7 +1231,15 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, kCtasPerSm) aecm_call_kerne
     const int row = blockIdx.x * kWarpsPerCta + warp;
     const bool live = row < a.count;
     if (!live && !kLockstep) return;
-    const int inst = a.first + (live ? row : 0);
+    int inst = a.first + (live ? row : 0);
+    if (a.index && live) {  // scattered rows (combined scalar calls): the row names its instance
+        inst = __ldg(&a.index[row]);
+        if ((unsigned)inst >= (unsigned)planes.n_instances) {
+            if (a.status && lane == 0) a.status[row] = AECM_BAD_PARAMETER_ERROR;
+            if (!kLockstep) return;
+            inst = 0;
+        }
+    }
     const bool use_clean = a.near_clean != nullptr;
     const uint32_t rec_bytes = use_clean ? AECM_STATE_BYTES : AECM_STATE_BYTES_NOCLEAN;
     AecmInstanceState *g_state = planes.state + inst;

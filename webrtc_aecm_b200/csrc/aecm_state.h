@@ -147,6 +147,7 @@ typedef struct {
     int32_t n_calls;        /* fused consecutive 10 ms calls */
     int32_t ms_uniform;
     int32_t mask_stride;    /* entries between consecutive calls in far_mask (>= count) */
+    const int32_t *index;   /* optional [count]: plane row r belongs to instance index[r] (distinct); `first` unused */
 } AecmCallArgs;
 
 /* all return a cudaError_t value (0 = success); launches are asynchronous on `stream` */

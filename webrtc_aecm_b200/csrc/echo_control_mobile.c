@@ -3,6 +3,16 @@
  * thin views over slots of device-resident batches.  Handles are small host descriptors; the AECM state and
  * every bit of arithmetic live on the GPU (aecm_kernels.cu).  Error codes and their precedence follow
  * aecm/echo_control_mobile.cc line by line (cited below).
+ *
+ * Threading.  The reference keeps all state inside the instance, so a program may drive different instances from
+ * different threads at the same time; the same holds here.  Instances share a batch (256 to a pool), and a batch
+ * takes one caller at a time, so every entry point serialises on its pool.  BufferFarend/Process calls go through a
+ * COMBINER: a caller queues its request; whoever finds no round in progress becomes the leader, takes everything
+ * queued so far (requests of all threads, for different instances), packs the audio rows into pinned staging
+ * planes and issues them as ONE launch per kind (rows name their instances through
+ * AecmB200StreamArgs.instanceIndex), hands the results back and repeats until the queue is empty.  T threads
+ * calling concurrently therefore cost about one launch + one PCIe round trip per round, not T of them
+ * ("batching of scalar WebRtcAecm_Process calls into lockstep launches").
  */
 #include <pthread.h>
 #include <stdlib.h>
@@ -13,11 +23,37 @@
 #define POOL_SLOTS 256
 #define HANDLE_MAGIC 0x41454342u /* "AECB" */
 
+#define MAX_SAMPLES 160
+
+enum { REQ_FAR = 0, REQ_PROC = 1 };
+
+typedef struct Req {
+    int kind;
+    int32_t slot;
+    const int16_t *far, *near_noisy, *near_clean;
+    int16_t *out;
+    int n;
+    int16_t ms;
+    int32_t result;
+    int done;
+    struct Req *next;
+} Req;
+
 typedef struct Pool {
     AecmB200Batch *batch;
     unsigned char used[POOL_SLOTS];
     int n_used;
     struct Pool *next;
+    /* the combiner */
+    pthread_mutex_t q_lock; /* queue, leader flag, Req.done */
+    pthread_cond_t q_cond;
+    Req *head, *tail;
+    int leader;
+    pthread_mutex_t exec;   /* held by whoever is talking to the batch */
+    int16_t *h_far, *h_near, *h_clean, *h_out; /* pinned, [POOL_SLOTS][MAX_SAMPLES] */
+    int32_t index[POOL_SLOTS], status[POOL_SLOTS];
+    int16_t ms[POOL_SLOTS];
+    long rounds, combined;  /* statistics: rounds run, requests served */
 } Pool;
 
 typedef struct {
@@ -43,11 +79,23 @@ void *WebRtcAecm_Create(void) { /* echo_control_mobile.cc:89-117 */
     if (!p) {
         p = (Pool *)calloc(1, sizeof(Pool));
         if (p) {
+            const size_t plane = (size_t)POOL_SLOTS * MAX_SAMPLES * sizeof(int16_t);
             p->batch = AecmB200_Create(POOL_SLOTS, default_device());
-            if (!p->batch) {
+            if (p->batch) {
+                p->h_far = (int16_t *)AecmB200_HostAlloc(plane);
+                p->h_near = (int16_t *)AecmB200_HostAlloc(plane);
+                p->h_clean = (int16_t *)AecmB200_HostAlloc(plane);
+                p->h_out = (int16_t *)AecmB200_HostAlloc(plane);
+            }
+            if (!p->batch || !p->h_far || !p->h_near || !p->h_clean || !p->h_out) {
+                AecmB200_HostFree(p->h_far); AecmB200_HostFree(p->h_near); AecmB200_HostFree(p->h_clean); AecmB200_HostFree(p->h_out);
+                AecmB200_Free(p->batch);
                 free(p);
                 p = NULL;
             } else {
+                pthread_mutex_init(&p->q_lock, NULL);
+                pthread_cond_init(&p->q_cond, NULL);
+                pthread_mutex_init(&p->exec, NULL);
                 p->next = g_pools;
                 g_pools = p;
             }
@@ -57,9 +105,13 @@ void *WebRtcAecm_Create(void) { /* echo_control_mobile.cc:89-117 */
         for (s = 0; p->used[s]; s++) {}
         h = (Handle *)calloc(1, sizeof(Handle));
         /* a fresh instance is zero-filled and un-initialised, like the reference's calloc (:91) */
-        if (h && AecmB200_Reset(p->batch, s, 1) != 0) {
-            free(h);
-            h = NULL;
+        if (h) {
+            pthread_mutex_lock(&p->exec);
+            if (AecmB200_Reset(p->batch, s, 1) != 0) {
+                free(h);
+                h = NULL;
+            }
+            pthread_mutex_unlock(&p->exec);
         }
         if (h) {
             p->used[s] = 1;
@@ -89,39 +141,169 @@ int32_t WebRtcAecm_Init(void *inst, int32_t sampFreq) { /* echo_control_mobile.c
     int32_t rc;
     if (!h) return -1;
     if (sampFreq != 8000 && sampFreq != 16000) return AECM_BAD_PARAMETER_ERROR;
+    pthread_mutex_lock(&h->pool->exec);
     rc = AecmB200_Init(h->pool->batch, h->slot, 1, sampFreq);
-    if (rc) return rc;
-    return AecmB200_Synchronize(h->pool->batch) ? AECM_UNSPECIFIED_ERROR : 0;
+    if (!rc) rc = AecmB200_Synchronize(h->pool->batch) ? AECM_UNSPECIFIED_ERROR : 0;
+    pthread_mutex_unlock(&h->pool->exec);
+    return rc;
 }
 
-static int32_t one_call(Handle *h, const int16_t *far, const int16_t *near_noisy, const int16_t *near_clean, int16_t *out,
-                        size_t n, int16_t ms) {
+/* One launch for every request of `kind` / `n` / clean-or-not in the round.  Rows are packed densely from row `r0` of
+ * the pinned planes; `slot` alternates so that the copies of one group overlap the kernel of another. */
+static void issue_group(Pool *p, Req **reqs, int count, int r0, int slot) {
     AecmB200StreamArgs a;
-    int32_t status = 0, rc;
+    const Req *q0 = reqs[0];
+    const int n = q0->n;
+    const size_t base = (size_t)r0 * MAX_SAMPLES;
+    int32_t rc;
+    int i;
+    for (i = 0; i < count; i++) {
+        const Req *q = reqs[i];
+        p->index[r0 + i] = q->slot;
+        p->ms[r0 + i] = q->ms;
+        p->status[r0 + i] = 0;
+        if (q->kind == REQ_FAR) {
+            memcpy(p->h_far + base + (size_t)i * n, q->far, (size_t)n * sizeof(int16_t));
+        } else {
+            memcpy(p->h_near + base + (size_t)i * n, q->near_noisy, (size_t)n * sizeof(int16_t));
+            if (q->near_clean) memcpy(p->h_clean + base + (size_t)i * n, q->near_clean, (size_t)n * sizeof(int16_t));
+        }
+    }
     memset(&a, 0, sizeof(a));
-    a.farend = far;
-    a.nearendNoisy = near_noisy;
-    a.nearendClean = near_clean;
-    a.out = out;
-    a.rowStride = (int64_t)n;
-    a.first = h->slot;
-    a.count = 1;
-    a.nrOfSamples = (int32_t)n;
+    if (q0->kind == REQ_FAR) {
+        a.farend = p->h_far + base;
+    } else {
+        a.nearendNoisy = p->h_near + base;
+        a.nearendClean = q0->near_clean ? p->h_clean + base : NULL;
+        a.out = p->h_out + base;
+    }
+    a.rowStride = n;
+    a.count = count;
+    a.nrOfSamples = n;
     a.nCalls = 1;
-    a.msUniform = ms;
-    a.status = &status;
-    rc = AecmB200_ProcessStream(h->pool->batch, &a);
-    return rc ? rc : status;
+    a.msInSndCardBuf = p->ms + r0;
+    a.status = p->status + r0;
+    a.instanceIndex = p->index + r0;
+    rc = AecmB200_WaitStream(p->batch, slot);
+    if (!rc) rc = AecmB200_SubmitStream(p->batch, &a, slot);
+    for (i = 0; i < count; i++) reqs[i]->result = rc; /* 0 = in flight: the per-row status follows in collect_group */
+}
+
+static void collect_group(Pool *p, Req **reqs, int count, int r0, int slot) {
+    const int32_t rc = AecmB200_WaitStream(p->batch, slot);
+    int i;
+    for (i = 0; i < count; i++) {
+        Req *q = reqs[i];
+        if (q->result) continue; /* the submission itself failed */
+        if (rc) { q->result = rc; continue; }
+        q->result = p->status[r0 + i];
+        if (q->kind == REQ_PROC) memcpy(q->out, p->h_out + (size_t)r0 * MAX_SAMPLES + (size_t)i * q->n, (size_t)q->n * sizeof(int16_t));
+    }
+}
+
+/* One round: the leader owns `list` (at most POOL_SLOTS requests on distinct instances). */
+static void run_round(Pool *p, Req *list) {
+    Req *group[8][POOL_SLOTS];
+    int count[8] = {0}, r0[8], pending[16], g, rows = 0, issued = 0, s;
+    const int n_slots = AecmB200_NumStreamSlots() < 16 ? AecmB200_NumStreamSlots() : 16;
+    Req *q;
+    for (q = list; q; q = q->next) { /* kind x frame size x clean-or-not: a launch is uniform in all three */
+        g = q->kind * 4 + (q->n == 160 ? 2 : 0) + (q->near_clean ? 1 : 0);
+        group[g][count[g]++] = q;
+    }
+    for (s = 0; s < n_slots; s++) pending[s] = -1;
+    pthread_mutex_lock(&p->exec);
+    for (g = 0; g < 8; g++) { /* BufferFarend groups first; the copies of one group overlap the kernel of another */
+        if (!count[g]) continue;
+        s = issued++ % n_slots;
+        if (pending[s] >= 0) collect_group(p, group[pending[s]], count[pending[s]], r0[pending[s]], s);
+        r0[g] = rows;
+        rows += count[g];
+        issue_group(p, group[g], count[g], r0[g], s);
+        pending[s] = g;
+    }
+    for (s = 0; s < n_slots; s++)
+        if (pending[s] >= 0) collect_group(p, group[pending[s]], count[pending[s]], r0[pending[s]], s);
+    pthread_mutex_unlock(&p->exec);
+}
+
+/* Queue the request and wait for its result; lead a round if nobody is. */
+static int32_t combine(Pool *p, Req *r) {
+    r->done = 0;
+    r->next = NULL;
+    pthread_mutex_lock(&p->q_lock);
+    if (p->tail) p->tail->next = r; else p->head = r;
+    p->tail = r;
+    while (!r->done) {
+        if (p->leader) {
+            pthread_cond_wait(&p->q_cond, &p->q_lock);
+            continue;
+        }
+        p->leader = 1;
+        while (p->head) {
+            /* take up to POOL_SLOTS requests on distinct instances, in arrival order; a second request for an instance
+             * already in the round (two threads on one instance) stays queued for the next round */
+            unsigned char seen[POOL_SLOTS] = {0};
+            Req *list = NULL, *list_tail = NULL, *keep = NULL, *keep_tail = NULL, *q = p->head, *nx;
+            int taken = 0;
+            for (; q; q = nx) {
+                nx = q->next;
+                q->next = NULL;
+                if (taken < POOL_SLOTS && !seen[q->slot]) {
+                    seen[q->slot] = 1;
+                    taken++;
+                    if (list_tail) list_tail->next = q; else list = q;
+                    list_tail = q;
+                } else {
+                    if (keep_tail) keep_tail->next = q; else keep = q;
+                    keep_tail = q;
+                }
+            }
+            p->head = keep;
+            p->tail = keep_tail;
+            pthread_mutex_unlock(&p->q_lock);
+            run_round(p, list);
+            pthread_mutex_lock(&p->q_lock);
+            p->rounds++;
+            for (q = list; q; q = nx) {
+                nx = q->next; /* the owner may free the request as soon as it sees done */
+                q->done = 1;
+                p->combined++;
+            }
+            pthread_cond_broadcast(&p->q_cond);
+        }
+        p->leader = 0;
+        pthread_cond_broadcast(&p->q_cond); /* a waiter whose request arrived too late takes over */
+    }
+    pthread_mutex_unlock(&p->q_lock);
+    return r->result;
+}
+
+/* initFlag lives on the device: GetEchoPath reports AECM_UNINITIALIZED_ERROR exactly when it is unset */
+static int is_uninitialized(Handle *h) {
+    int16_t path[65];
+    int32_t rc;
+    pthread_mutex_lock(&h->pool->exec);
+    rc = AecmB200_GetEchoPath(h->pool->batch, h->slot, path, sizeof(path));
+    pthread_mutex_unlock(&h->pool->exec);
+    return rc == AECM_UNINITIALIZED_ERROR;
+}
+
+/* diagnostics for the tests: rounds run and requests served by the combiner of the pool `inst` lives in */
+void AecmB200_ScalarApiStats(void *inst, int64_t *rounds, int64_t *requests) {
+    Handle *h = (Handle *)inst;
+    if (!h) return;
+    pthread_mutex_lock(&h->pool->q_lock);
+    if (rounds) *rounds = h->pool->rounds;
+    if (requests) *requests = h->pool->combined;
+    pthread_mutex_unlock(&h->pool->q_lock);
 }
 
 int32_t WebRtcAecm_GetBufferFarendError(void *inst, const int16_t *farend, size_t n) { /* :195-213 */
     Handle *h = (Handle *)inst;
-    int16_t path[65];
     if (!h) return -1;
     if (!farend) return AECM_NULL_POINTER_ERROR;
-    /* initFlag lives on the device: GetEchoPath reports AECM_UNINITIALIZED_ERROR exactly when it is unset */
-    if (AecmB200_GetEchoPath(h->pool->batch, h->slot, path, sizeof(path)) == AECM_UNINITIALIZED_ERROR)
-        return AECM_UNINITIALIZED_ERROR;
+    if (is_uninitialized(h)) return AECM_UNINITIALIZED_ERROR;
     if (n != 80 && n != 160) return AECM_BAD_PARAMETER_ERROR;
     return 0;
 }
@@ -135,7 +317,15 @@ int32_t WebRtcAecm_BufferFarend(void *inst, const int16_t *farend, size_t n) { /
         const int32_t e = WebRtcAecm_GetBufferFarendError(inst, farend, n);
         return e ? e : AECM_BAD_PARAMETER_ERROR;
     }
-    return one_call(h, farend, NULL, NULL, NULL, n, 0);
+    {
+        Req r;
+        memset(&r, 0, sizeof(r));
+        r.kind = REQ_FAR;
+        r.slot = h->slot;
+        r.far = farend;
+        r.n = (int)n;
+        return combine(h->pool, &r);
+    }
 }
 
 int32_t WebRtcAecm_Process(void *inst, const int16_t *near_noisy, const int16_t *near_clean, int16_t *out, size_t n,
@@ -145,30 +335,49 @@ int32_t WebRtcAecm_Process(void *inst, const int16_t *near_noisy, const int16_t 
     if (!near_noisy) return AECM_NULL_POINTER_ERROR;
     if (!out) return AECM_NULL_POINTER_ERROR;
     if (n != 80 && n != 160) {
-        int16_t path[65];
-        if (AecmB200_GetEchoPath(h->pool->batch, h->slot, path, sizeof(path)) == AECM_UNINITIALIZED_ERROR)
-            return AECM_UNINITIALIZED_ERROR; /* :264-266 precedes :268-270 */
+        if (is_uninitialized(h)) return AECM_UNINITIALIZED_ERROR; /* :264-266 precedes :268-270 */
         return AECM_BAD_PARAMETER_ERROR;
     }
-    return one_call(h, NULL, near_noisy, near_clean, out, n, ms);
+    {
+        Req r;
+        memset(&r, 0, sizeof(r));
+        r.kind = REQ_PROC;
+        r.slot = h->slot;
+        r.near_noisy = near_noisy;
+        r.near_clean = near_clean;
+        r.out = out;
+        r.n = (int)n;
+        r.ms = ms;
+        return combine(h->pool, &r);
+    }
 }
 
 int32_t WebRtcAecm_set_config(void *inst, AecmConfig config) { /* :410-479 */
     Handle *h = (Handle *)inst;
     int32_t status = 0, rc;
     if (!h) return -1;
+    pthread_mutex_lock(&h->pool->exec);
     rc = AecmB200_SetConfig(h->pool->batch, h->slot, 1, config, &status);
+    pthread_mutex_unlock(&h->pool->exec);
     return rc ? rc : status;
 }
 
 int32_t WebRtcAecm_InitEchoPath(void *inst, const void *echo_path, size_t size_bytes) { /* :481-503 */
     Handle *h = (Handle *)inst;
+    int32_t rc;
     if (!h) return -1;
-    return AecmB200_InitEchoPath(h->pool->batch, h->slot, echo_path, size_bytes);
+    pthread_mutex_lock(&h->pool->exec);
+    rc = AecmB200_InitEchoPath(h->pool->batch, h->slot, echo_path, size_bytes);
+    pthread_mutex_unlock(&h->pool->exec);
+    return rc;
 }
 
 int32_t WebRtcAecm_GetEchoPath(void *inst, void *echo_path, size_t size_bytes) { /* :505-528 */
     Handle *h = (Handle *)inst;
+    int32_t rc;
     if (!h) return -1;
-    return AecmB200_GetEchoPath(h->pool->batch, h->slot, echo_path, size_bytes);
+    pthread_mutex_lock(&h->pool->exec);
+    rc = AecmB200_GetEchoPath(h->pool->batch, h->slot, echo_path, size_bytes);
+    pthread_mutex_unlock(&h->pool->exec);
+    return rc;
 }
