@@ -152,8 +152,11 @@ typedef struct {
     int32_t use_clean;       /* pass the clean plane */
     int32_t n_threads;
     int32_t skip_far_every;  /* >0: skip BufferFarend on calls where (call % skip)==skip-1 (underrun) */
+    int32_t ms_per_call;     /* !=0: ms is [n_instances][n_calls], one msInSndCardBuf per call */
+    int32_t extra_far_every; /* >0: BufferFarend is called TWICE (same frame) where (call % k)==k-1 (overrun) */
 } OracleRunConfig;
-/* planes are [n_instances][n_calls*samples_per_call] int16; ms is [n_instances] or NULL (=40);
+/* planes are [n_instances][n_calls*samples_per_call] int16; ms is [n_instances] (or [n_instances][n_calls] with
+ * ms_per_call) or NULL (=40);
  * ret_or is [n_instances] OR of all return codes. impl: 0 = this oracle, 1 = reference library at
  * ref_lib_path (dlopen, RTLD_LOCAL). Returns 0, or <0 on setup failure. */
 int oracle_run_streams(const OracleRunConfig *cfg, int impl, const char *ref_lib_path,

@@ -3,7 +3,10 @@
 Each case is a dict of API-level parameters; ``make_inputs(case)`` builds the int16 planes deterministically.
 The families follow SURVEY.md section 8(c): both rates, echoMode 0-4, CNG on/off, clean path, stress audio
 (silence / full scale / clipping), msInSndCardBuf extremes incl. clamped values, far-end underrun, both
-frame sizes at both rates, and the per-instance delay sweep of BASELINE.json configs[4]."""
+frame sizes at both rates, the per-instance delay sweep of BASELINE.json configs[4], and -- found with
+tools/ref_coverage.py (gcov over the reference) -- msInSndCardBuf that changes from call to call (start-up
+stability check, EstBufDelay's delay-change logic), far-end overrun (two BufferFarend per Process), a constant
+far level (minimum step size) and a near end that stays a few LSB for half a minute (noise-floor counters)."""
 from __future__ import annotations
 
 import numpy as np
@@ -15,7 +18,7 @@ MS_MIX = [0, 40, 120, 500, -5, 600, 10, 250]
 
 def _c(name, **kw):
     d = dict(name=name, fs=16000, spc=None, n=4, seconds=4.0, echo_mode=3, cng=1, clean=False, kind="echo", ms=None,
-             skip_far_every=0, delay_ms="sweep20", seed=101, special=None)
+             skip_far_every=0, extra_far_every=0, ms_schedule=None, delay_ms="sweep20", seed=101, special=None)
     d.update(kw)
     if d["spc"] is None:
         d["spc"] = 160 if d["fs"] == 16000 else 80
@@ -51,6 +54,14 @@ CASES = [
     _c("8k_adv_gated_tone_dc_near_mode0", fs=8000, special="adv_gated", seconds=12.0, seed=300, echo_mode=0, cng=0),
     _c("8k_adv_tone_far_whisper_near", fs=8000, special="adv_whisper", seconds=12.0, seed=303, echo_mode=0, cng=0),
     _c("16k_adv_loud_far_zero_near_mode4", special="adv_zero_near", seconds=12.0, seed=304, echo_mode=4, ms=[0, 120, 500, 40]),
+    # families added after measuring which reference lines the cases above never reach (oracle/COVERAGE.md)
+    _c("16k_ms_jumps", ms_schedule="jumps", seconds=8.0, seed=400),          # echo_control_mobile.cc:552-566
+    _c("8k_ms_jumps_underrun", fs=8000, ms_schedule="jumps", skip_far_every=5, seconds=8.0, seed=401),
+    _c("16k_ms_unstable_startup", ms_schedule="startup", seconds=3.0, seed=402, n=8),  # :305-337
+    _c("16k_far_overrun", extra_far_every=3, seed=410, seconds=6.0),         # :543-546 (two BufferFarend per Process)
+    _c("8k_far_overrun_ms_jumps", fs=8000, extra_far_every=2, ms_schedule="jumps", seed=411, seconds=6.0),
+    _c("8k_constant_far_level", fs=8000, special="const_far", seconds=6.0, seed=420),   # aecm_core.cc:778-779
+    _c("8k_near_few_lsb_30s", fs=8000, special="tiny_near", seconds=30.0, seed=430, n=2),  # aecm_core_c.cc:117-124
 ]
 CASE_BY_NAME = {c["name"]: c for c in CASES}
 
@@ -93,8 +104,50 @@ def make_inputs(case):
     clean = None
     if case["clean"]:
         clean = synth_streams(n, total, fs, seed=case["seed"] + 1000, delay_ms=10, kind="echo")[1]
+    elif case["special"] == "const_far":   # stationary far end: min and max trackers of the far energy meet
+        rng = np.random.default_rng(case["seed"])
+        far = rng.integers(-4000, 4000, size=(n, total)).astype(np.int16)
+        near = (far // 3 + rng.integers(-20, 20, size=(n, total))).astype(np.int16)
+    elif case["special"] == "tiny_near":   # the near end stays within a few LSB: the noise-floor estimate creeps
+        rng = np.random.default_rng(case["seed"])
+        near = rng.integers(-2, 3, size=(n, total)).astype(np.int16)
     ms = None if case["ms"] is None else np.resize(np.asarray(case["ms"], dtype=np.int16), n)
+    if case["ms_schedule"]:
+        ms = ms_schedule(case, total // case["spc"])
     return far, near, clean, ms
+
+
+def ms_schedule(case, n_calls):
+    """[n, n_calls] int16: msInSndCardBuf per call.  'jumps': piecewise constant with large steps both ways every
+    0.3-1 s (per instance its own pattern); 'startup': values that wobble by more than the +-20 % / 8 ms tolerance during
+    the first calls, then settle -- each instance settles at a different call."""
+    n = case["n"]
+    rng = np.random.default_rng(case["seed"] + 7)
+    ms = np.zeros((n, n_calls), dtype=np.int16)
+    if case["ms_schedule"] == "jumps":
+        levels = np.array([0, 10, 40, 60, 120, 200, 350, 500, 20, 480, 33, 77], dtype=np.int16)
+        for i in range(n):
+            c = 0
+            while c < n_calls:
+                seg = int(rng.integers(30, 100))
+                ms[i, c:c + seg] = levels[int(rng.integers(0, len(levels)))]
+                c += seg
+                if rng.random() < 0.5:  # a two-call spike to the top followed by a drop to zero (one-call swings of the
+                    ms[i, c:c + 2] = 500  # filtered delay across both EstBufDelay thresholds)
+                    ms[i, c + 2:c + 4] = 0
+                    c += 4
+    else:
+        for i in range(n):
+            settle = 2 + 7 * i  # instance 0 settles at once, the last one only after the 0.5 s give-up limit
+            ms[i, :] = 40 + 10 * i
+            ms[i, :settle] = rng.choice([5, 40, 150, 300, 90], size=min(settle, n_calls))[:n_calls]
+    return ms
+
+
+def run_kwargs(case):
+    """The case's API-level parameters as keyword arguments of oracle_lib.run_streams."""
+    return dict(fs=case["fs"], samples_per_call=case["spc"], cng_mode=case["cng"], echo_mode=case["echo_mode"],
+                skip_far_every=case["skip_far_every"], extra_far_every=case["extra_far_every"])
 
 
 def far_mask(case, n_calls):

@@ -21,7 +21,8 @@ REF_SO = os.path.join(ORACLE_DIR, "_ref", "libaecm_ref.so")
 class RunConfig(C.Structure):
     _fields_ = [("n_instances", C.c_int32), ("fs", C.c_int32), ("samples_per_call", C.c_int32),
                 ("n_calls", C.c_int32), ("cng_mode", C.c_int32), ("echo_mode", C.c_int32),
-                ("use_clean", C.c_int32), ("n_threads", C.c_int32), ("skip_far_every", C.c_int32)]
+                ("use_clean", C.c_int32), ("n_threads", C.c_int32), ("skip_far_every", C.c_int32),
+                ("ms_per_call", C.c_int32), ("extra_far_every", C.c_int32)]
 
 
 _lib = None
@@ -79,7 +80,7 @@ def _ptr(a):
 
 
 def run_streams(far, near, *, fs=16000, samples_per_call=None, impl="oracle", clean=None, ms=None, cng_mode=1,
-                echo_mode=3, threads=None, skip_far_every=0):
+                echo_mode=3, threads=None, skip_far_every=0, extra_far_every=0):
     """Run [n, T] int16 planes through the oracle ('oracle') or the reference library ('ref').
 
     Returns (out[n, T] int16, ret_or[n] int32, seconds)."""
@@ -88,11 +89,15 @@ def run_streams(far, near, *, fs=16000, samples_per_call=None, impl="oracle", cl
     n, total = far.shape
     spc = samples_per_call or (160 if fs == 16000 else 80)
     assert total % spc == 0
+    per_call = ms is not None and np.ndim(ms) == 2  # [n, n_calls]: one msInSndCardBuf per call
     cfg = RunConfig(n, fs, spc, total // spc, cng_mode, echo_mode, 0 if clean is None else 1,
-                    threads or min(os.cpu_count() or 1, max(n, 1)), skip_far_every)
+                    threads or min(os.cpu_count() or 1, max(n, 1)), skip_far_every, 1 if per_call else 0, extra_far_every)
     if clean is not None:
         clean = np.ascontiguousarray(clean, dtype=np.int16)
-    if ms is not None:
+    if per_call:
+        ms = np.ascontiguousarray(ms, dtype=np.int16)
+        assert ms.shape == (n, total // spc)
+    elif ms is not None:
         ms = np.ascontiguousarray(np.broadcast_to(np.asarray(ms, dtype=np.int16), (n,)))
     out = np.zeros_like(near)
     ret = np.zeros(n, dtype=np.int32)

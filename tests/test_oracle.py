@@ -9,7 +9,7 @@ import numpy as np
 import pytest
 
 import oracle_lib as ol
-from cases import CASES, make_inputs
+from cases import CASES, make_inputs, run_kwargs
 from webrtc_aecm_b200.shard import stream_checksum
 
 GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
@@ -19,8 +19,7 @@ VEC = np.load(os.path.join(GOLD, "vectors.npz"))
 
 def run_case(case, impl):
     far, near, clean, ms = make_inputs(case)
-    out, ret, _ = ol.run_streams(far, near, fs=case["fs"], samples_per_call=case["spc"], impl=impl, clean=clean, ms=ms,
-                                 cng_mode=case["cng"], echo_mode=case["echo_mode"], skip_far_every=case["skip_far_every"])
+    out, ret, _ = ol.run_streams(far, near, impl=impl, clean=clean, ms=ms, **run_kwargs(case))
     return far, near, out, ret
 
 

@@ -23,7 +23,7 @@ sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 import oracle_lib as ol  # noqa: E402
-from cases import CASES, make_inputs  # noqa: E402
+from cases import CASES, make_inputs, run_kwargs  # noqa: E402
 from webrtc_aecm_b200.shard import stream_checksum  # noqa: E402
 
 FULL_VECTOR_CASES = ("16k_80_sample_calls", "16k_full_scale_alternating")
@@ -81,9 +81,7 @@ def main():
     vectors = {}
     for case in CASES:
         far, near, clean, ms = make_inputs(case)
-        out, ret, _ = ol.run_streams(far, near, fs=case["fs"], samples_per_call=case["spc"], impl="ref", clean=clean,
-                                     ms=ms, cng_mode=case["cng"], echo_mode=case["echo_mode"],
-                                     skip_far_every=case["skip_far_every"])
+        out, ret, _ = ol.run_streams(far, near, impl="ref", clean=clean, ms=ms, **run_kwargs(case))
         streams[case["name"]] = {"sha256": stream_checksum(out), "ret_or": [int(r) for r in ret],
                                  "shape": list(out.shape), "inputs_sha256": stream_checksum(np.concatenate([far, near]))}
         if case["name"] in FULL_VECTOR_CASES:

@@ -16,9 +16,11 @@
  * end of its buffer).
  *
  * Ragged lengths: the pairs of one rate are sorted longest first, so the set of instances that still have frames
- * left is always a prefix [0, live) of the batch; launches cover [t, next) calls where `next` is the next point at
- * which an instance runs out (or --chunk-calls further on).  With several devices the sorted pairs are dealt
- * round-robin, one host thread per device, each double-buffering its host<->device copies against its kernels
+ * left is always a prefix [0, live) of the batch.  The batch advances in chunks of --chunk-calls 10 ms calls, one
+ * kernel launch per chunk; a stream that ends inside a chunk runs on into silence for the rest of that chunk (its
+ * output there is dropped) and is gone from the next one.  Chunks are staged through two sets of pinned planes, so the
+ * host-side packing of chunk k+1, the PCIe copies and the kernel of chunk k overlap.  With several devices the sorted
+ * pairs are dealt round-robin, one host thread per device
  * (AecmB200_SubmitStream / AecmB200_WaitStream).  No CPU fallback: without a CUDA device the tool fails. */
 #define _GNU_SOURCE
 #include <errno.h>
@@ -176,88 +178,102 @@ typedef struct {
 static int collect(Shard *s, AecmB200Batch *b, int slot, const int32_t *status, int *pending) {
     const int count = *pending;
     int i, rc = AecmB200_WaitStream(b, slot);
-    *pending = 0;
     if (rc) { snprintf(s->err, sizeof(s->err), "WaitStream failed with %d: %s", rc, AecmB200_LastError(b)); return -1; }
     for (i = 0; i < count; i++)
         if (status[i]) { snprintf(s->err, sizeof(s->err), "%s: WebRtcAecm_Process returned %d", s->pairs[i]->near_path, status[i]); return -1; }
     return 0;
 }
 
+/* copy the chunk [t, t + calls) of every live row into (fill != 0) or out of the slot's pinned staging planes */
+static void stage_chunk(Shard *s, int live, int64_t t, int calls, int16_t *far, int16_t *near, const int16_t *out, int fill) {
+    const size_t spc = (size_t)s->spc, width = (size_t)calls * spc;
+    int i;
+    for (i = 0; i < live; i++) {
+        Pair *p = s->pairs[i];
+        const int64_t left = p->n_calls - t; /* > 0 for a live row */
+        const size_t have = (size_t)(left < calls ? left : calls) * spc, at = (size_t)t * spc;
+        if (fill) {
+            size_t have_far = p->n_far > at ? (size_t)(p->n_far - at) : 0; /* a short far file is continued with silence */
+            if (have_far > have) have_far = have;
+            memcpy(far + i * width, p->far + at, have_far * 2);
+            memset(far + i * width + have_far, 0, (width - have_far) * 2);
+            memcpy(near + i * width, p->near + at, have * 2);
+            memset(near + i * width + have, 0, (width - have) * 2); /* a row that ends inside the chunk runs on into silence */
+        } else {
+            memcpy(p->near + at, out + i * width, have * 2); /* main.cc:141 */
+        }
+    }
+}
+
 static void *run_shard(void *arg) {
     Shard *s = (Shard *)arg;
     const Options *o = s->opt;
-    const int n = s->n, spc = s->spc;
+    const int n = s->n, spc = s->spc, K = o->chunk_calls;
     const int64_t max_calls = n ? s->pairs[0]->n_calls : 0;
-    const size_t row = (size_t)max_calls * (size_t)spc;
+    const size_t plane = (size_t)n * (size_t)K * (size_t)spc * sizeof(int16_t);
     AecmB200Batch *b = NULL;
-    int16_t *far = NULL, *near = NULL, *out = NULL;
+    int16_t *far[2] = {NULL, NULL}, *near[2] = {NULL, NULL}, *out[2] = {NULL, NULL};
     int32_t *status[2] = {NULL, NULL};
+    int64_t t_of[2] = {0, 0}, t = 0;
     AecmConfig cfg;
-    int64_t t = 0;
-    int live = n, k = 0, i, rc, pending[2] = {0, 0}; /* pending[slot] = instances of the submission in flight */
+    int live = n, k = 0, i, rc, pending[2] = {0, 0}; /* pending[slot] = live rows of the chunk in flight there */
     if (n == 0 || max_calls == 0) return NULL;
     b = AecmB200_Create(n, s->device);
     if (!b) { snprintf(s->err, sizeof(s->err), "AecmB200_Create(%d instances, device %d) failed", n, s->device); s->failed = 1; return NULL; }
-    far = (int16_t *)AecmB200_HostAlloc(n * row * 2);
-    near = (int16_t *)AecmB200_HostAlloc(n * row * 2);
-    out = (int16_t *)AecmB200_HostAlloc(n * row * 2);
-    status[0] = (int32_t *)calloc((size_t)n, sizeof(int32_t));
-    status[1] = (int32_t *)calloc((size_t)n, sizeof(int32_t));
-    if (!far || !near || !out || !status[0] || !status[1]) { snprintf(s->err, sizeof(s->err), "out of pinned host memory (%zu bytes per plane)", n * row * 2); goto fail; }
-    for (i = 0; i < n; i++) { /* rows: whole frames only, far padded with silence */
-        const Pair *p = s->pairs[i];
-        const size_t used = (size_t)p->n_calls * (size_t)spc, have_far = p->n_far < used ? (size_t)p->n_far : used;
-        memset(far + i * row, 0, row * 2);
-        memset(near + i * row, 0, row * 2);
-        memcpy(far + i * row, p->far, have_far * 2);
-        memcpy(near + i * row, p->near, used * 2);
+    for (i = 0; i < 2; i++) { /* pinned staging for two chunks in flight; far and near adjacent: one transfer for both */
+        far[i] = (int16_t *)AecmB200_HostAlloc(2 * plane);
+        out[i] = (int16_t *)AecmB200_HostAlloc(plane);
+        status[i] = (int32_t *)calloc((size_t)n, sizeof(int32_t));
+        if (!far[i] || !out[i] || !status[i]) { snprintf(s->err, sizeof(s->err), "out of pinned host memory (%zu bytes per plane)", plane); goto fail; }
     }
     cfg.cngMode = (int16_t)o->cng;
     cfg.echoMode = (int16_t)o->echo_mode;
     rc = AecmB200_Init(b, 0, n, (int32_t)s->rate);
     if (!rc) rc = AecmB200_SetConfig(b, 0, n, cfg, NULL);
     if (rc) { snprintf(s->err, sizeof(s->err), "init/set_config failed with %d: %s", rc, AecmB200_LastError(b)); goto fail; }
-    while (live > 0 && s->pairs[live - 1]->n_calls <= t) live--;
-    while (live > 0) {
+    for (t = 0; t < max_calls; t += K, k++) {
         AecmB200StreamArgs a;
-        int64_t next = s->pairs[live - 1]->n_calls; /* the shortest of the live instances ends here */
         const int slot = k & 1;
-        if (next > t + o->chunk_calls) next = t + o->chunk_calls;
-        if (pending[slot] && collect(s, b, slot, status[slot], &pending[slot])) goto fail;
+        while (live > 0 && s->pairs[live - 1]->n_calls <= t) live--; /* sorted longest first: the live rows are a prefix */
+        if (pending[slot]) { /* results of the chunk before last */
+            int count = pending[slot];
+            if (collect(s, b, slot, status[slot], &count)) goto fail;
+            stage_chunk(s, pending[slot], t_of[slot], K, NULL, NULL, out[slot], 0);
+            pending[slot] = 0;
+        }
+        near[slot] = far[slot] + (size_t)live * (size_t)K * (size_t)spc;
+        stage_chunk(s, live, t, K, far[slot], near[slot], NULL, 1);
         memset(&a, 0, sizeof(a));
-        a.farend = far + t * spc;
-        a.nearendNoisy = near + t * spc;
-        a.out = out + t * spc;
-        a.rowStride = (int64_t)row;
+        a.farend = far[slot];
+        a.nearendNoisy = near[slot];
+        a.out = out[slot];
+        a.rowStride = (int64_t)K * spc;
         a.first = 0;
         a.count = live;
         a.nrOfSamples = spc;
-        a.nCalls = (int32_t)(next - t);
+        a.nCalls = K;
         a.msUniform = (int16_t)o->ms;
         a.status = status[slot];
         rc = AecmB200_SubmitStream(b, &a, slot);
         if (rc) { snprintf(s->err, sizeof(s->err), "SubmitStream failed with %d: %s", rc, AecmB200_LastError(b)); goto fail; }
         pending[slot] = live;
+        t_of[slot] = t;
         s->launches++;
-        t = next;
-        k++;
-        while (live > 0 && s->pairs[live - 1]->n_calls <= t) live--;
     }
     for (i = 0; i < 2; i++) {
         const int slot = (k + i) & 1; /* oldest first */
-        if (pending[slot] && collect(s, b, slot, status[slot], &pending[slot])) goto fail;
+        int count = pending[slot];
+        if (!count) continue;
+        if (collect(s, b, slot, status[slot], &count)) goto fail;
+        stage_chunk(s, pending[slot], t_of[slot], K, NULL, NULL, out[slot], 0);
+        pending[slot] = 0;
     }
-    for (i = 0; i < n; i++) {
-        Pair *p = s->pairs[i];
-        memcpy(p->near, out + i * row, (size_t)p->n_calls * (size_t)spc * 2); /* main.cc:141 */
-        s->blocks_done += p->n_calls * spc / 64;
-    }
+    for (i = 0; i < n; i++) s->blocks_done += s->pairs[i]->n_calls * spc / 64;
     goto done;
 fail:
     s->failed = 1;
 done:
-    AecmB200_HostFree(far); AecmB200_HostFree(near); AecmB200_HostFree(out);
-    free(status[0]); free(status[1]);
+    for (i = 0; i < 2; i++) { AecmB200_HostFree(far[i]); AecmB200_HostFree(out[i]); free(status[i]); }
     AecmB200_Free(b);
     return NULL;
 }
