@@ -10,7 +10,8 @@
  * COMBINER: a caller queues its request; whoever finds no round in progress becomes the leader, takes everything
  * queued so far (requests of all threads, for different instances), packs the audio rows into pinned staging
  * planes and issues them as ONE launch per kind (rows name their instances through
- * AecmB200StreamArgs.instanceIndex), hands the results back and repeats until the queue is empty.  T threads
+ * AecmB200StreamArgs.instanceIndex), hands each result back to its owner and repeats until its own request has been
+ * served; then the oldest request still queued is woken to lead the next round.  T threads
  * calling concurrently therefore cost about one launch + one PCIe round trip per round, not T of them
  * ("batching of scalar WebRtcAecm_Process calls into lockstep launches").
  */
@@ -36,6 +37,7 @@ typedef struct Req {
     int16_t ms;
     int32_t result;
     int done;
+    pthread_cond_t cond; /* signalled when done, or when this request's owner should take over as leader */
     struct Req *next;
 } Req;
 
@@ -46,7 +48,6 @@ typedef struct Pool {
     struct Pool *next;
     /* the combiner */
     pthread_mutex_t q_lock; /* queue, leader flag, Req.done */
-    pthread_cond_t q_cond;
     Req *head, *tail;
     int leader;
     pthread_mutex_t exec;   /* held by whoever is talking to the batch */
@@ -94,7 +95,6 @@ void *WebRtcAecm_Create(void) { /* echo_control_mobile.cc:89-117 */
                 p = NULL;
             } else {
                 pthread_mutex_init(&p->q_lock, NULL);
-                pthread_cond_init(&p->q_cond, NULL);
                 pthread_mutex_init(&p->exec, NULL);
                 p->next = g_pools;
                 g_pools = p;
@@ -231,16 +231,17 @@ static void run_round(Pool *p, Req *list) {
 static int32_t combine(Pool *p, Req *r) {
     r->done = 0;
     r->next = NULL;
+    pthread_cond_init(&r->cond, NULL);
     pthread_mutex_lock(&p->q_lock);
     if (p->tail) p->tail->next = r; else p->head = r;
     p->tail = r;
     while (!r->done) {
-        if (p->leader) {
-            pthread_cond_wait(&p->q_cond, &p->q_lock);
+        if (p->leader) { /* sleeps until its result is in, or until leadership is handed to it */
+            pthread_cond_wait(&r->cond, &p->q_lock);
             continue;
         }
         p->leader = 1;
-        while (p->head) {
+        while (!r->done && p->head) { /* lead until the own request has been served (it is still queued until then) */
             /* take up to POOL_SLOTS requests on distinct instances, in arrival order; a second request for an instance
              * already in the round (two threads on one instance) stays queued for the next round */
             unsigned char seen[POOL_SLOTS] = {0};
@@ -266,16 +267,17 @@ static int32_t combine(Pool *p, Req *r) {
             pthread_mutex_lock(&p->q_lock);
             p->rounds++;
             for (q = list; q; q = nx) {
-                nx = q->next; /* the owner may free the request as soon as it sees done */
+                nx = q->next; /* the owner may release the request as soon as it sees done */
                 q->done = 1;
                 p->combined++;
+                if (q != r) pthread_cond_signal(&q->cond); /* only the owner wakes up */
             }
-            pthread_cond_broadcast(&p->q_cond);
         }
         p->leader = 0;
-        pthread_cond_broadcast(&p->q_cond); /* a waiter whose request arrived too late takes over */
+        if (p->head) pthread_cond_signal(&p->head->cond); /* requests that arrived meanwhile: the oldest one leads next */
     }
     pthread_mutex_unlock(&p->q_lock);
+    pthread_cond_destroy(&r->cond);
     return r->result;
 }
 
