@@ -11,6 +11,7 @@
 // 100 delay candidates -> 4 strided passes.  Warp-uniform state-machine code is computed redundantly by all lanes in
 // registers (no broadcasts); the scalars themselves are read from the shared-memory record and written back by lane 0
 // only, with __syncwarp() between the last read and the write and after it (compute-sanitizer racecheck: 0 hazards).
+#include <atomic>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -1397,7 +1398,7 @@ __global__ void aecm_init_echo_path_kernel(AecmBatchPlanes planes, int first, in
     if (status && lane == 0) status[row] = r;
 }
 
-int g_launches = 0;
+std::atomic<int> g_launches{0};  // launches may come from several host threads (one per device, or the scalar-API leader)
 
 }  // namespace
 
@@ -1422,7 +1423,7 @@ __global__ void aecm_sqrt_selftest_kernel(uint32_t first, uint32_t count, unsign
 
 extern "C" {
 
-int aecm_cuda_kernel_launch_count(void) { return g_launches; }
+int aecm_cuda_kernel_launch_count(void) { return g_launches.load(); }
 
 int aecm_cuda_launch_init(const AecmBatchPlanes *p, int first, int count, int samp_freq, void *stream) {
     if (count <= 0) return 0;
@@ -1459,7 +1460,7 @@ int aecm_cuda_launch_init_echo_path(const AecmBatchPlanes *p, int first, int cou
 
 int aecm_cuda_launch_call(const AecmBatchPlanes *p, const AecmCallArgs *a, void *stream) {
     if (a->count <= 0 || a->n_calls <= 0) return 0;
-    static bool attr_set[64] = {};  // function attributes are per device
+    static std::atomic<bool> attr_set[64];  // function attributes are per device
     const size_t smem = (size_t)kWarpsPerCta * (sizeof(AecmInstanceState) + sizeof(WarpScratch));
     int dev = 0;
     if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return (int)cudaErrorInvalidDevice;
