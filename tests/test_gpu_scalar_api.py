@@ -158,8 +158,78 @@ def test_scalar_api_from_many_threads_is_combined_and_bit_exact():
     r1, q1 = C.c_int64(0), C.c_int64(0)
     L.AecmB200_ScalarApiStats(hs[0], C.byref(r1), C.byref(q1))
     requests, rounds = q1.value - q0.value, r1.value - r0.value
-    assert requests == 2 * T * calls
+    assert requests == T * calls  # every Process carried the far-end frame buffered just before it
     assert rounds < requests, (rounds, requests)  # some rounds carried more than one request
     print(f"combiner: {requests} requests in {rounds} rounds ({requests / rounds:.1f} per round)")
     for h in hs:
         L.WebRtcAecm_Free(h)
+
+
+def test_deferred_far_end_keeps_the_callers_order():
+    """BufferFarend only validates and parks the frame; it travels with the next call on that instance.  Irregular
+    call orders must still behave like the reference: two BufferFarend in a row, 80-sample far frames before a
+    160-sample Process, control calls in between, an Init that drops what was buffered, Process without any far end."""
+    from webrtc_aecm_b200 import api
+
+    L = api.scalar_api()
+    fs = 16000
+    far, near = synth_streams(1, 160 * 400, fs, seed=77, delay_ms=25)
+    far, near = far[0], near[0]
+    h = L.WebRtcAecm_Create()
+    o = ol.OracleInstance(fs, 1, 3)
+    assert L.WebRtcAecm_Init(h, fs) == 0 and L.WebRtcAecm_set_config(h, api.AecmConfig(1, 3)) == 0
+    lib = ol.oracle()
+    rng = np.random.default_rng(5)
+    pos = 0
+
+    def both_far(n):
+        nonlocal pos
+        f = np.ascontiguousarray(far[pos:pos + n])
+        assert L.WebRtcAecm_BufferFarend(h, P(f), n) == 0
+        assert o.buffer_farend(f) == 0
+
+    def both_process(n, ms):
+        nonlocal pos
+        x = np.ascontiguousarray(near[pos:pos + n])
+        out = np.zeros_like(x)
+        rc = L.WebRtcAecm_Process(h, P(x), None, P(out), n, ms)
+        want_rc, want = o.process(x, None, ms)
+        assert rc == want_rc
+        np.testing.assert_array_equal(out, want)
+        pos += n
+
+    for step in range(300):
+        kind = int(rng.integers(0, 8))
+        if kind == 0:      # far-end overrun: two frames before one Process
+            both_far(160)
+            both_far(160)
+            both_process(160, 40)
+        elif kind == 1:    # two 80-sample far frames, one 160-sample Process
+            both_far(80)
+            pos += 80
+            both_far(80)
+            pos -= 80
+            both_process(160, 40)
+        elif kind == 2:    # far-end underrun
+            both_process(160, 60)
+        elif kind == 3:    # control calls between BufferFarend and Process
+            both_far(160)
+            got, want = np.zeros(65, np.int16), np.zeros(65, np.int16)
+            assert L.WebRtcAecm_GetEchoPath(h, P(got), 130) == 0
+            assert lib.oracle_aecm_get_echo_path(o.h, want.ctypes.data_as(C.c_void_p), 130) == 0
+            np.testing.assert_array_equal(got, want)
+            assert L.WebRtcAecm_set_config(h, api.AecmConfig(1, 3)) == 0
+            assert lib.oracle_aecm_set_config(o.h, 1, 3) == 0
+            both_process(160, 40)
+        elif kind == 4 and step % 50 == 49:  # re-Init with a frame still parked: it is dropped, like everything buffered
+            both_far(160)
+            assert L.WebRtcAecm_Init(h, fs) == 0 and lib.oracle_aecm_init(o.h, fs) == 0
+            both_process(160, 40)
+        elif kind == 5:    # 80-sample calls at 16 kHz
+            both_far(80)
+            both_process(80, 40)
+        else:              # the regular pattern
+            both_far(160)
+            both_process(160, 40)
+    L.WebRtcAecm_Free(h)
+    o.close()

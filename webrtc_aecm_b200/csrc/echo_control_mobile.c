@@ -14,6 +14,14 @@
  * served; then the oldest request still queued is woken to lead the next round.  T threads
  * calling concurrently therefore cost about one launch + one PCIe round trip per round, not T of them
  * ("batching of scalar WebRtcAecm_Process calls into lockstep launches").
+ *
+ * Deferred far end.  WebRtcAecm_BufferFarend can only fail on its arguments or on an un-initialised instance
+ * (echo_control_mobile.cc:195-213), all of which the host knows (initFlag is mirrored in the handle: only Init sets
+ * it, only Create clears it).  So the call validates, keeps the frame in the handle and returns; the frame travels
+ * with the NEXT request of that instance -- normally the WebRtcAecm_Process that follows, which then runs
+ * BufferFarend + Process in ONE launch, in the reference's order.  Anything else that touches the instance first
+ * (a second BufferFarend, a different frame size, set_config, the echo-path calls) sends the pending frame ahead
+ * on its own; Init and Free drop it, as the reference's Init drops everything buffered (:163-166).
  */
 #include <pthread.h>
 #include <stdlib.h>
@@ -26,12 +34,10 @@
 
 #define MAX_SAMPLES 160
 
-enum { REQ_FAR = 0, REQ_PROC = 1 };
 
 typedef struct Req {
-    int kind;
     int32_t slot;
-    const int16_t *far, *near_noisy, *near_clean;
+    const int16_t *far, *near_noisy, *near_clean; /* far only = BufferFarend; near (+ far) = [BufferFarend +] Process */
     int16_t *out;
     int n;
     int16_t ms;
@@ -61,6 +67,9 @@ typedef struct {
     uint32_t magic;
     Pool *pool;
     int32_t slot;
+    int initialized;            /* host mirror of the device's initFlag */
+    int pending_n;              /* samples of a far-end frame accepted by BufferFarend but not yet sent (0 = none) */
+    int16_t pending[MAX_SAMPLES];
 } Handle;
 
 static Pool *g_pools = NULL;
@@ -141,14 +150,16 @@ int32_t WebRtcAecm_Init(void *inst, int32_t sampFreq) { /* echo_control_mobile.c
     int32_t rc;
     if (!h) return -1;
     if (sampFreq != 8000 && sampFreq != 16000) return AECM_BAD_PARAMETER_ERROR;
+    h->pending_n = 0; /* Init empties the far-end buffer (:163-166): a frame not yet sent is dropped with it */
     pthread_mutex_lock(&h->pool->exec);
     rc = AecmB200_Init(h->pool->batch, h->slot, 1, sampFreq);
     if (!rc) rc = AecmB200_Synchronize(h->pool->batch) ? AECM_UNSPECIFIED_ERROR : 0;
     pthread_mutex_unlock(&h->pool->exec);
+    if (!rc) h->initialized = 1;
     return rc;
 }
 
-/* One launch for every request of `kind` / `n` / clean-or-not in the round.  Rows are packed densely from row `r0` of
+/* One launch for every request of the same shape (far / near / both, frame size, clean-or-not) in the round.  Rows are packed densely from row `r0` of
  * the pinned planes; `slot` alternates so that the copies of one group overlap the kernel of another. */
 static void issue_group(Pool *p, Req **reqs, int count, int r0, int slot) {
     AecmB200StreamArgs a;
@@ -162,17 +173,13 @@ static void issue_group(Pool *p, Req **reqs, int count, int r0, int slot) {
         p->index[r0 + i] = q->slot;
         p->ms[r0 + i] = q->ms;
         p->status[r0 + i] = 0;
-        if (q->kind == REQ_FAR) {
-            memcpy(p->h_far + base + (size_t)i * n, q->far, (size_t)n * sizeof(int16_t));
-        } else {
-            memcpy(p->h_near + base + (size_t)i * n, q->near_noisy, (size_t)n * sizeof(int16_t));
-            if (q->near_clean) memcpy(p->h_clean + base + (size_t)i * n, q->near_clean, (size_t)n * sizeof(int16_t));
-        }
+        if (q->far) memcpy(p->h_far + base + (size_t)i * n, q->far, (size_t)n * sizeof(int16_t));
+        if (q->near_noisy) memcpy(p->h_near + base + (size_t)i * n, q->near_noisy, (size_t)n * sizeof(int16_t));
+        if (q->near_clean) memcpy(p->h_clean + base + (size_t)i * n, q->near_clean, (size_t)n * sizeof(int16_t));
     }
     memset(&a, 0, sizeof(a));
-    if (q0->kind == REQ_FAR) {
-        a.farend = p->h_far + base;
-    } else {
+    if (q0->far) a.farend = p->h_far + base;
+    if (q0->near_noisy) {
         a.nearendNoisy = p->h_near + base;
         a.nearendClean = q0->near_clean ? p->h_clean + base : NULL;
         a.out = p->h_out + base;
@@ -197,23 +204,23 @@ static void collect_group(Pool *p, Req **reqs, int count, int r0, int slot) {
         if (q->result) continue; /* the submission itself failed */
         if (rc) { q->result = rc; continue; }
         q->result = p->status[r0 + i];
-        if (q->kind == REQ_PROC) memcpy(q->out, p->h_out + (size_t)r0 * MAX_SAMPLES + (size_t)i * q->n, (size_t)q->n * sizeof(int16_t));
+        if (q->near_noisy) memcpy(q->out, p->h_out + (size_t)r0 * MAX_SAMPLES + (size_t)i * q->n, (size_t)q->n * sizeof(int16_t));
     }
 }
 
 /* One round: the leader owns `list` (at most POOL_SLOTS requests on distinct instances). */
 static void run_round(Pool *p, Req *list) {
-    Req *group[8][POOL_SLOTS];
-    int count[8] = {0}, r0[8], pending[16], g, rows = 0, issued = 0, s;
+    Req *group[12][POOL_SLOTS];
+    int count[12] = {0}, r0[12], pending[16], g, rows = 0, issued = 0, s;
     const int n_slots = AecmB200_NumStreamSlots() < 16 ? AecmB200_NumStreamSlots() : 16;
     Req *q;
-    for (q = list; q; q = q->next) { /* kind x frame size x clean-or-not: a launch is uniform in all three */
-        g = q->kind * 4 + (q->n == 160 ? 2 : 0) + (q->near_clean ? 1 : 0);
+    for (q = list; q; q = q->next) { /* far-only / near-only / both x frame size x clean-or-not: a launch is uniform in all */
+        g = (q->near_noisy ? (q->far ? 2 : 1) : 0) * 4 + (q->n == 160 ? 2 : 0) + (q->near_clean ? 1 : 0);
         group[g][count[g]++] = q;
     }
     for (s = 0; s < n_slots; s++) pending[s] = -1;
     pthread_mutex_lock(&p->exec);
-    for (g = 0; g < 8; g++) { /* BufferFarend groups first; the copies of one group overlap the kernel of another */
+    for (g = 0; g < 12; g++) { /* the copies of one group overlap the kernel of another */
         if (!count[g]) continue;
         s = issued++ % n_slots;
         if (pending[s] >= 0) collect_group(p, group[pending[s]], count[pending[s]], r0[pending[s]], s);
@@ -281,14 +288,16 @@ static int32_t combine(Pool *p, Req *r) {
     return r->result;
 }
 
-/* initFlag lives on the device: GetEchoPath reports AECM_UNINITIALIZED_ERROR exactly when it is unset */
-static int is_uninitialized(Handle *h) {
-    int16_t path[65];
-    int32_t rc;
-    pthread_mutex_lock(&h->pool->exec);
-    rc = AecmB200_GetEchoPath(h->pool->batch, h->slot, path, sizeof(path));
-    pthread_mutex_unlock(&h->pool->exec);
-    return rc == AECM_UNINITIALIZED_ERROR;
+/* send a far-end frame that was accepted earlier on its own (it cannot ride with a Process call) */
+static int32_t flush_pending(Handle *h) {
+    Req r;
+    if (!h->pending_n) return 0;
+    memset(&r, 0, sizeof(r));
+    r.slot = h->slot;
+    r.far = h->pending;
+    r.n = h->pending_n;
+    h->pending_n = 0;
+    return combine(h->pool, &r);
 }
 
 /* diagnostics for the tests: rounds run and requests served by the combiner of the pool `inst` lives in */
@@ -305,59 +314,56 @@ int32_t WebRtcAecm_GetBufferFarendError(void *inst, const int16_t *farend, size_
     Handle *h = (Handle *)inst;
     if (!h) return -1;
     if (!farend) return AECM_NULL_POINTER_ERROR;
-    if (is_uninitialized(h)) return AECM_UNINITIALIZED_ERROR;
+    if (!h->initialized) return AECM_UNINITIALIZED_ERROR;
     if (n != 80 && n != 160) return AECM_BAD_PARAMETER_ERROR;
     return 0;
 }
 
 int32_t WebRtcAecm_BufferFarend(void *inst, const int16_t *farend, size_t n) { /* :215-234 */
     Handle *h = (Handle *)inst;
-    if (!h) return -1;
-    if (!farend) return AECM_NULL_POINTER_ERROR;
-    if (n != 80 && n != 160) {
-        /* precedence: the reference reports UNINITIALIZED before BAD_PARAMETER (:205-210) */
-        const int32_t e = WebRtcAecm_GetBufferFarendError(inst, farend, n);
-        return e ? e : AECM_BAD_PARAMETER_ERROR;
-    }
-    {
-        Req r;
-        memset(&r, 0, sizeof(r));
-        r.kind = REQ_FAR;
-        r.slot = h->slot;
-        r.far = farend;
-        r.n = (int)n;
-        return combine(h->pool, &r);
-    }
+    int32_t rc = WebRtcAecm_GetBufferFarendError(inst, farend, n); /* :221-225: the only ways this call can fail */
+    if (rc) return rc;
+    rc = flush_pending(h); /* a frame is already waiting (two BufferFarend in a row): it goes first, on its own */
+    if (rc) return rc;
+    memcpy(h->pending, farend, n * sizeof(int16_t)); /* rides with the next Process of this instance */
+    h->pending_n = (int)n;
+    return 0;
 }
 
 int32_t WebRtcAecm_Process(void *inst, const int16_t *near_noisy, const int16_t *near_clean, int16_t *out, size_t n,
                            int16_t ms) { /* :236-408 */
     Handle *h = (Handle *)inst;
+    Req r;
+    int32_t rc;
     if (!h) return -1;
     if (!near_noisy) return AECM_NULL_POINTER_ERROR;
     if (!out) return AECM_NULL_POINTER_ERROR;
-    if (n != 80 && n != 160) {
-        if (is_uninitialized(h)) return AECM_UNINITIALIZED_ERROR; /* :264-266 precedes :268-270 */
-        return AECM_BAD_PARAMETER_ERROR;
+    if (!h->initialized) return AECM_UNINITIALIZED_ERROR; /* :264-266 precedes :268-270 */
+    if (n != 80 && n != 160) return AECM_BAD_PARAMETER_ERROR;
+    memset(&r, 0, sizeof(r));
+    r.slot = h->slot;
+    if (h->pending_n == (int)n) {
+        r.far = h->pending; /* BufferFarend + Process in one launch, in the reference's order */
+    } else {
+        rc = flush_pending(h); /* another frame size: a launch has one */
+        if (rc) return rc;
     }
-    {
-        Req r;
-        memset(&r, 0, sizeof(r));
-        r.kind = REQ_PROC;
-        r.slot = h->slot;
-        r.near_noisy = near_noisy;
-        r.near_clean = near_clean;
-        r.out = out;
-        r.n = (int)n;
-        r.ms = ms;
-        return combine(h->pool, &r);
-    }
+    r.near_noisy = near_noisy;
+    r.near_clean = near_clean;
+    r.out = out;
+    r.n = (int)n;
+    r.ms = ms;
+    rc = combine(h->pool, &r);
+    h->pending_n = 0;
+    return rc;
 }
 
 int32_t WebRtcAecm_set_config(void *inst, AecmConfig config) { /* :410-479 */
     Handle *h = (Handle *)inst;
     int32_t status = 0, rc;
     if (!h) return -1;
+    rc = flush_pending(h); /* keep the caller's order of operations on this instance */
+    if (rc) return rc;
     pthread_mutex_lock(&h->pool->exec);
     rc = AecmB200_SetConfig(h->pool->batch, h->slot, 1, config, &status);
     pthread_mutex_unlock(&h->pool->exec);
@@ -368,6 +374,8 @@ int32_t WebRtcAecm_InitEchoPath(void *inst, const void *echo_path, size_t size_b
     Handle *h = (Handle *)inst;
     int32_t rc;
     if (!h) return -1;
+    rc = flush_pending(h); /* keep the caller's order of operations on this instance */
+    if (rc) return rc;
     pthread_mutex_lock(&h->pool->exec);
     rc = AecmB200_InitEchoPath(h->pool->batch, h->slot, echo_path, size_bytes);
     pthread_mutex_unlock(&h->pool->exec);
@@ -378,6 +386,8 @@ int32_t WebRtcAecm_GetEchoPath(void *inst, void *echo_path, size_t size_bytes) {
     Handle *h = (Handle *)inst;
     int32_t rc;
     if (!h) return -1;
+    rc = flush_pending(h); /* keep the caller's order of operations on this instance */
+    if (rc) return rc;
     pthread_mutex_lock(&h->pool->exec);
     rc = AecmB200_GetEchoPath(h->pool->batch, h->slot, echo_path, size_bytes);
     pthread_mutex_unlock(&h->pool->exec);
