@@ -28,7 +28,7 @@ constexpr unsigned kFull = 0xffffffffu;
 #define AECM_WARPS_PER_CTA 28
 #endif
 constexpr int kWarpsPerCta = AECM_WARPS_PER_CTA;
-constexpr int kCtasPerSm = 28 / kWarpsPerCta;
+constexpr int kCtasPerSm = kWarpsPerCta >= 28 ? 1 : 28 / kWarpsPerCta;
 #ifndef AECM_LOCKSTEP
 #define AECM_LOCKSTEP 0
 #endif
