@@ -105,6 +105,9 @@ AecmB200Batch *AecmB200_GroupShard(const AecmB200Group *group, int32_t shard, in
 int32_t AecmB200_GroupInit(AecmB200Group *group, int32_t sampFreq);
 int32_t AecmB200_GroupSetConfig(AecmB200Group *group, AecmConfig config, int32_t *status);
 int32_t AecmB200_GroupProcessStream(AecmB200Group *group, const AecmB200StreamArgs *hostArgs);
+/* the pipelined form, as AecmB200_SubmitStream / AecmB200_WaitStream: every shard works on its slice in slot `slot` */
+int32_t AecmB200_GroupSubmitStream(AecmB200Group *group, const AecmB200StreamArgs *hostArgs, int32_t slot);
+int32_t AecmB200_GroupWaitStream(AecmB200Group *group, int32_t slot);
 
 /* stream plumbing: the batch owns a CUDA stream unless one is adopted (e.g. the caller's current stream) */
 int32_t AecmB200_Synchronize(AecmB200Batch *batch);

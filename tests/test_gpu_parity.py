@@ -344,4 +344,17 @@ def test_group_sharding_over_devices_matches_oracle():
     a = api.StreamArgs(f.ctypes.data, nr.ctypes.data, None, o.ctypes.data, f.shape[1], 2, 8, spc, 1, None, 40, None, None)
     assert L.AecmB200_GroupProcessStream(g, C.byref(a)) == 0
     assert L.AecmB200_GroupProcessStream(g, None) == 12003
+    # the pipelined form: fresh state, one 10 ms call per submission, two slots in flight on every shard
+    assert L.AecmB200_GroupInit(g, fs) == 0
+    assert L.AecmB200_GroupSetConfig(g, api.AecmConfig(1, 3), st.ctypes.data) == 0
+    hf = np.ascontiguousarray(far.reshape(n, calls, spc).transpose(1, 0, 2))
+    hn = np.ascontiguousarray(near.reshape(n, calls, spc).transpose(1, 0, 2))
+    ho = np.zeros_like(hn)
+    for k in range(calls):
+        a = api.StreamArgs(hf[k].ctypes.data, hn[k].ctypes.data, None, ho[k].ctypes.data, spc, 0, n, spc, 1, None, 40, None, None)
+        assert L.AecmB200_GroupSubmitStream(g, C.byref(a), k % 2) == 0
+        if k:
+            assert L.AecmB200_GroupWaitStream(g, (k - 1) % 2) == 0
+    assert L.AecmB200_GroupWaitStream(g, (calls - 1) % 2) == 0
+    np.testing.assert_array_equal(ho.transpose(1, 0, 2).reshape(n, calls * spc), want)
     L.AecmB200_GroupFree(g)

@@ -1,5 +1,5 @@
 #!/usr/bin/env python3
-"""Executed warp-instructions per source *section* of aecm_kernels.cu (sections = '// ----' banner comments
+"""Executed warp-instructions per source *section* of the device code (aecm_kernels.cu and its .cuh files) (sections = '// ----' banner comments
 and function heads), from an ncu report captured with --import-source on.  Usage:
     python tools/ncu_regions.py gpurun_out/prof.ncu-rep 20480"""
 import collections, csv, io, re, subprocess, sys

@@ -96,6 +96,7 @@ def lib():
             "AecmB200_GroupShard": (vp, [vp, i32, C.POINTER(i32), C.POINTER(i32)]),
             "AecmB200_GroupInit": (i32, [vp, i32]), "AecmB200_GroupSetConfig": (i32, [vp, AecmConfig, vp]),
             "AecmB200_GroupProcessStream": (i32, [vp, C.POINTER(StreamArgs)]),
+            "AecmB200_GroupSubmitStream": (i32, [vp, C.POINTER(StreamArgs), i32]), "AecmB200_GroupWaitStream": (i32, [vp, i32]),
             "AecmB200_BufferFarend": (i32, [vp, vp, C.c_size_t, vp]),
             "AecmB200_Process": (i32, [vp, vp, vp, vp, C.c_size_t, vp, C.c_int16, vp]),
             "AecmB200_Synchronize": (i32, [vp]), "AecmB200_CudaStream": (vp, [vp]),

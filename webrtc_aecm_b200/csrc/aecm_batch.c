@@ -600,14 +600,15 @@ int32_t AecmB200_GroupSetConfig(AecmB200Group *g, AecmConfig cfg, int32_t *statu
     return 0;
 }
 
-int32_t AecmB200_GroupProcessStream(AecmB200Group *g, const AecmB200StreamArgs *h) {
+/* the shard-local slice of the caller's range goes to every device on stream slot `slot` */
+int32_t AecmB200_GroupSubmitStream(AecmB200Group *g, const AecmB200StreamArgs *h, int32_t slot) {
     int i;
     int32_t rc = 0, worst = 0;
     if (!g) return -1;
     if (!h) return AECM_NULL_POINTER_ERROR;
     if (h->first < 0 || h->count < 0 || (int64_t)h->first + h->count > g->n) return AECM_BAD_PARAMETER_ERROR;
     if (h->farendMask || h->instanceIndex) return AECM_UNSUPPORTED_FUNCTION_ERROR; /* both are laid out over the whole range */
-    for (i = 0; i < g->n_shards; i++) { /* submit the shard-local slice of the range to every device ... */
+    for (i = 0; i < g->n_shards; i++) {
         const int32_t lo = h->first > g->first[i] ? h->first : g->first[i];
         const int32_t hi = h->first + h->count < g->first[i + 1] ? h->first + h->count : g->first[i + 1];
         AecmB200StreamArgs a = *h;
@@ -621,12 +622,30 @@ int32_t AecmB200_GroupProcessStream(AecmB200Group *g, const AecmB200StreamArgs *
         if (h->out) a.out = h->out + row * h->rowStride;
         if (h->msInSndCardBuf) a.msInSndCardBuf = h->msInSndCardBuf + row;
         if (h->status) a.status = h->status + row;
-        rc = AecmB200_SubmitStream(g->shard[i], &a, 0);
-        if (rc) worst = rc;
-    }
-    for (i = 0; i < g->n_shards; i++) { /* ... then collect */
-        rc = AecmB200_WaitStream(g->shard[i], 0);
+        rc = AecmB200_SubmitStream(g->shard[i], &a, slot);
         if (rc) worst = rc;
     }
     return worst;
+}
+
+int32_t AecmB200_GroupWaitStream(AecmB200Group *g, int32_t slot) {
+    int i;
+    int32_t rc, worst = 0;
+    if (!g) return -1;
+    for (i = 0; i < g->n_shards; i++) {
+        rc = AecmB200_WaitStream(g->shard[i], slot);
+        if (rc) worst = rc;
+    }
+    return worst;
+}
+
+/* submit to all devices, then collect */
+int32_t AecmB200_GroupProcessStream(AecmB200Group *g, const AecmB200StreamArgs *h) {
+    int32_t rc, rc2;
+    if (!g) return -1;
+    rc = AecmB200_GroupWaitStream(g, 0); /* keep submission order if the caller mixes the two styles */
+    if (rc) return rc;
+    rc = AecmB200_GroupSubmitStream(g, h, 0);
+    rc2 = AecmB200_GroupWaitStream(g, 0);
+    return rc ? rc : rc2;
 }

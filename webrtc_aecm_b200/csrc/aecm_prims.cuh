@@ -1,0 +1,206 @@
+// aecm_prims.cuh -- launch shape, algorithm constants, compile-time tables, per-warp scratch, scalar primitives
+// (part of the single device translation unit aecm_kernels.cu; see that file's header for the mapping)
+#ifndef AECM_PRIMS_CUH_
+#define AECM_PRIMS_CUH_
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "aecm_fft.cuh"
+#include "aecm_state.h"
+#include "aecm_tables.h"
+
+namespace {
+
+constexpr unsigned kFull = 0xffffffffu;
+// One 28-warp CTA per SM: the warps of an SM start together and drift less through the ~50 KB of straight-line
+// code than seven independent 4-warp CTAs do (measured: +26 % throughput), at identical residency.
+#ifndef AECM_WARPS_PER_CTA
+#define AECM_WARPS_PER_CTA 28
+#endif
+constexpr int kWarpsPerCta = AECM_WARPS_PER_CTA;
+constexpr int kCtasPerSm = kWarpsPerCta >= 28 ? 1 : 28 / kWarpsPerCta;
+#ifndef AECM_LOCKSTEP
+#define AECM_LOCKSTEP 0
+#endif
+constexpr bool kLockstep = AECM_LOCKSTEP != 0;  // CTA-wide rendezvous before every block (I-cache locality experiment)  // 28 warps/SM: BASELINE configs[1] (4096 instances) is a single wave on 148 SMs
+
+// ---- algorithm constants, aecm_defines.h:28-85 ----
+constexpr int kConvLen = 512;
+constexpr int kFarEnergyMin = 1025;
+constexpr int kFarEnergyDiff = 929;
+constexpr int kEnergyDevTol = 400;
+constexpr int kFarEnergyVadRegion = 230;
+constexpr int kMuMin = 10, kMuMax = 1, kMuDiff = 9;
+constexpr int kMinMseCount = 20, kMinMseDiff = 29, kMseResolution = 5;
+constexpr int kResCh16 = 12, kResCh32 = 28, kChannelVad = 16, kResSupGain = 8;
+constexpr int kSupGainDefault = 256, kSupGainA = 3072, kSupGainB = 1536, kSupGainD = 256, kSupGainEpcDt = 200;
+constexpr int kOneQ14 = 16384, kNlpLow = 3277;
+
+// LCG jump-ahead: after k steps of seed' = (seed*69069 + 1) mod 2^31 the seed is mul[k-1]*seed + add[k-1]
+// (signal_processing_library.cc:129-136), so lane-parallel code can draw the k-th number directly.
+struct LcgTable {
+    uint32_t mul[64], add[64];
+};
+constexpr LcgTable make_lcg_table() {
+    LcgTable t{};
+    uint32_t a = 1, c = 0;
+    for (int k = 0; k < 64; k++) {
+        c = c * 69069u + 1u;
+        a = a * 69069u;
+        t.mul[k] = a & 0x7fffffffu;
+        t.add[k] = c & 0x7fffffffu;
+    }
+    return t;
+}
+__device__ const LcgTable kLcgJump = make_lcg_table();
+
+// Per-lane constant words of the FFT tile layouts (aecm_fft.cuh), built at compile time.  All constant tables
+// stay in global memory and are read through the read-only path: they are a few KB, hit in L1 after first touch,
+// and cost neither shared memory nor a per-launch staging loop.
+struct LaneTables {
+    int4 words[32];  // aecm_fft::LaneWords {a, b, c, d}
+    int4 bins[32];   // aecm_fft::LaneBins {k0, k1, m0, m1}
+};
+constexpr LaneTables make_lane_tables() {
+    LaneTables t{};
+    for (int L = 0; L < 32; L++) {
+        t.words[L] = int4{aecm_fft::phys(4 * L), aecm_fft::phys((L >> 2) * 16 + (L & 3)),
+                          aecm_fft::phys((L >> 4) * 64 + (L & 15)), aecm_fft::phys(L)};
+        t.bins[L] = int4{aecm_fft::phys(aecm_fft::brev7c(L)), aecm_fft::phys(aecm_fft::brev7c(L + 32)),
+                         aecm_fft::phys(aecm_fft::brev7c((128 - L) & 127)), aecm_fft::phys(aecm_fft::brev7c(96 - L))};
+    }
+    return t;
+}
+__device__ const LaneTables kLaneTables = make_lane_tables();
+
+// Exact signed division by d = 2..65 (the NLMS normalisation by bin index + 1, aecm_core.cc:904) without a divide:
+// for 0 <= n <= 2^31 and 2^s <= d < 2^(s+1), floor(n / d) = (n * M) >> (32 + s') with M = ceil(2^(32+s') / d) < 2^32,
+// s' = s for non powers of two and s - 1 for powers of two (then M = 2^31 exactly).  Truncation toward zero for
+// negative dividends is restored by dividing |n|.
+struct DivTable {
+    uint32_t mul[66];
+    int32_t shift[66];
+};
+constexpr DivTable make_div_table() {
+    DivTable t{};
+    for (int d = 2; d <= 65; d++) {
+        int s = 0;
+        while ((2 << s) <= d) s++;          // 2^s <= d < 2^(s+1)
+        const bool pow2 = (1 << s) == d;
+        const int sp = pow2 ? s - 1 : s;
+        const unsigned long long num = 1ull << (32 + sp);
+        t.mul[d] = (uint32_t)((num + (unsigned)d - 1) / (unsigned)d);
+        t.shift[d] = sp;
+    }
+    return t;
+}
+__device__ const DivTable kDivTable = make_div_table();
+__device__ __forceinline__ int div_by_bin(int n, int d) {  // d = bin index + 1 in [1, 65]
+    if (d == 1) return n;
+    const uint32_t a = (uint32_t)abs(n);
+    const uint32_t q = __umulhi(a, __ldg(&kDivTable.mul[d])) >> __ldg(&kDivTable.shift[d]);
+    return n < 0 ? -(int)q : (int)q;
+}
+
+__device__ __forceinline__ const int2 *twiddle_table() { return reinterpret_cast<const int2 *>(kAecmTwiddleCS); }
+__device__ __forceinline__ int hann_q14(int i) { return __ldg(&kAecmSqrtHanningQ14[i]); }
+
+struct __align__(16) WarpScratch {
+    uint32_t fft[256];     // two 128-word transpose tiles of the register FFT (packed complex int16)
+    uint32_t dfw[68];      // near (or clean) spectrum after the sign flip of aecm_core_c.cc:188-190
+    int32_t echo_est[68];
+    uint16_t xfa[72], dfa_noisy[72], dfa_clean[72], far_row[72];
+    uint64_t mbar_a;       // mbarriers of the record's two bulk loads (part A: scalars/FIFOs, part B: the rest)
+    uint64_t mbar_b;
+};
+
+struct Ctx {
+    AecmInstanceState *st;  // shared-memory copy of the record
+    WarpScratch *sc;
+    uint16_t *far_hist;     // this instance's 100 x 66 rows in HBM
+    int16_t *far_ring;      // this instance's 4000-sample jitter FIFO in HBM
+    int lane;
+};
+
+// wait for a bulk load (phase 0 of its mbarrier); returns at once when the data already arrived
+__device__ __forceinline__ void mbar_wait(uint64_t *bar) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_RECORD:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], 0;\n"
+        "@p bra DONE_RECORD;\n"
+        "bra WAIT_RECORD;\n"
+        "DONE_RECORD:\n"
+        "}\n" ::"r"((uint32_t)__cvta_generic_to_shared(bar))
+        : "memory");
+}
+
+// ------------------------------------------------------------------------------------------------
+// scalar primitives (spl_inl.h, signal_processing_library.{h,cc})
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ int s16(int v) { return (int)(short)v; }  // int16 truncation + sign extension
+__device__ __forceinline__ int norm_w32(int a) { return a == 0 ? 0 : __clz(a < 0 ? ~a : a) - 1; }   // spl_inl.h:96
+__device__ __forceinline__ int norm_u32(unsigned a) { return a == 0 ? 0 : __clz((int)a); }          // spl_inl.h:101
+__device__ __forceinline__ int norm_w16(int a) { return a == 0 ? 0 : __clz(a < 0 ? ~a : a) - 17; } // spl_inl.h:107
+__device__ __forceinline__ int add_sat32(int a, int b) {  // spl_inl.h:70-82
+    int r;
+    asm("add.sat.s32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b));
+    return r;
+}
+__device__ __forceinline__ int sat16(int v) { return max(-32768, min(32767, v)); }  // spl_inl.h:59-68
+__device__ __forceinline__ uint32_t pack16(int lo, int hi) { return __byte_perm((uint32_t)lo, (uint32_t)hi, 0x5410); }
+__device__ __forceinline__ int lo16(uint32_t v) { return (int)(short)(v & 0xffffu); }
+__device__ __forceinline__ int hi16(uint32_t v) { return ((int)v) >> 16; }
+
+// WEBRTC_SPL_SHIFT_W32 (signal_processing_library.h:130).  The shift count of the NLMS rescaling
+// (aecm_core.cc:906-912) can leave [-31, 31]; the reference then executes an x86 SAR/SHL, which uses the
+// count modulo 32, so counts are masked here the same way (CUDA's native shifts clamp instead).
+__device__ __forceinline__ int shift_s32(int x, int c) {
+    return c >= 0 ? (int)((uint32_t)x << (c & 31)) : x >> ((-c) & 31);
+}
+__device__ __forceinline__ uint32_t shift_u32(uint32_t x, int c) { return c >= 0 ? x << (c & 31) : x >> ((-c) & 31); }
+
+// signal_processing_library.cc:84-105 is floor(sqrt(v)) for v in [0, 2^31).  One MUFU.SQRT
+// (relative error <= 2^-23: the estimate is within 0.01 of the root on this range) instead of the IEEE sqrtf sequence
+// with its slow-path call; the two integer corrections make the result exact for ANY estimate within +-1 of the root.
+// aecm_sqrt_selftest_kernel below sweeps all 2^31 arguments on the device (tests/test_gpu_parity.py).
+__device__ __forceinline__ int sqrt_floor(int v) {
+    float f;
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(f) : "f"(__uint2float_rn((uint32_t)v)));
+    uint32_t r = (uint32_t)__float2int_rz(f);
+    if (r * r > (uint32_t)v) r--;
+    if ((r + 1) * (r + 1) <= (uint32_t)v) r++;
+    return (int)r;
+}
+
+__device__ __forceinline__ void mean_estimator_fix(int v, int factor, int &mean) {  // delay_estimator.cc:690-702
+    int d = v - mean;
+    d = d < 0 ? -((-d) >> factor) : d >> factor;
+    mean += d;
+}
+
+__device__ __forceinline__ int log_energy_q8(uint32_t e, int q) {  // aecm_core.cc:612-628
+    int r = 7 << 7;
+    if (e > 0) {
+        const int z = __clz((int)e);
+        const int frac = (int)(((e << z) & 0x7fffffffu) >> 23);
+        r = s16(r + ((31 - z) << 8) + frac - (q << 8));
+    }
+    return r;
+}
+
+__device__ __forceinline__ int asym_filt(int old_v, int in, int step_pos, int step_neg) {  // aecm_core.cc:588-605
+    if (old_v == 32767 || old_v == -32768) return in;
+    return old_v > in ? s16(old_v - ((old_v - in) >> step_neg)) : s16(old_v + ((in - old_v) >> step_pos));
+}
+
+__device__ __forceinline__ int wrap_add(int base, int k, int cap) {  // (base + k) mod cap for 0 <= base,k < cap
+    const int v = base + k;
+    return v >= cap ? v - cap : v;
+}
+
+}  // namespace
+
+#endif  // AECM_PRIMS_CUH_
