@@ -145,6 +145,7 @@ def run_ours(args):
         raise SystemExit("bench.py: no CUDA device (the AECM engine has no CPU path)")
     from webrtc_aecm_b200.numa import bind_to_gpu
 
+    all_cpus = os.sched_getaffinity(0)
     n_local_cpus = bind_to_gpu(local)  # host planes are first-touched on the GPU's own socket
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
@@ -301,6 +302,7 @@ def run_ours(args):
     # ---- CPU baseline beside it (rank 0, N=1 only) ----
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        os.sched_setaffinity(0, all_cpus)  # the CPU reference gets every host core, not just the GPU's socket
         cpu = cpu_reference_throughput(fs, spc, n_inst=1024, prep_calls=PREP_CALLS, timed_calls=160)
 
     if rank == 0:
@@ -344,7 +346,7 @@ def cpu_reference_throughput(fs, spc, n_inst, prep_calls, timed_calls, threads=N
     import oracle_lib as ol
     from webrtc_aecm_b200.synth import synth_streams
 
-    threads = threads or (os.cpu_count() or 1)
+    threads = threads or len(os.sched_getaffinity(0))
     kind = "reference" if ol.ref_path() else "port"
     pool = ol.CpuPool(n_inst, fs=fs, impl="ref" if kind == "reference" else "oracle", cng_mode=1, echo_mode=3,
                       threads=threads)
@@ -381,10 +383,11 @@ def run_reference(args):
     import oracle_lib as ol
     from webrtc_aecm_b200.synth import synth_streams
 
-    threads = os.cpu_count() or 1
+    threads = len(os.sched_getaffinity(0))
     kind = "reference" if ol.ref_path() else "port"
-    # bounded sample of the workload: a slice of the batch sized so the run stays within a few minutes
-    n_inst = min(B, max(threads * 8, 256))
+    # bounded sample of the workload: a slice of the batch, sized for about two million blocks in the timed region
+    # (seconds of wall clock on a big host, so that starting the threads does not show) and at least 8 instances per thread
+    n_inst = min(B, max(threads * 8, 256, int(2e6 / (K * cps * spc / 64.0)) + 1))
     pool = ol.CpuPool(n_inst, fs=fs, impl="ref" if kind == "reference" else "oracle", threads=threads)
     total = PREP_CALLS + (W + K) * cps
     base = min(n_inst, 64)
