@@ -340,13 +340,34 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
+def usable_cpus():
+    """Host threads this process can really run at once: the affinity mask, capped by the cgroup CPU quota (a container
+    that sees 128 CPUs but is given 16 CPUs' worth of time gets slower, not faster, with 128 busy threads)."""
+    n = len(os.sched_getaffinity(0))
+    quota = None
+    try:
+        q, period = open("/sys/fs/cgroup/cpu.max").read().split()[:2]  # cgroup v2
+        if q != "max":
+            quota = float(q) / float(period)
+    except (OSError, ValueError):
+        try:
+            q = float(open("/sys/fs/cgroup/cpu/cpu.cfs_quota_us").read())  # cgroup v1
+            if q > 0:
+                quota = q / float(open("/sys/fs/cgroup/cpu/cpu.cfs_period_us").read())
+        except (OSError, ValueError):
+            pass
+    if quota:
+        n = max(1, min(n, int(quota + 0.999)))
+    return n
+
+
 def cpu_reference_throughput(fs, spc, n_inst, prep_calls, timed_calls, threads=None):
     """Blocks/s of the reference's C path on the host cores for the same workload (bounded sample)."""
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     import oracle_lib as ol
     from webrtc_aecm_b200.synth import synth_streams
 
-    threads = threads or len(os.sched_getaffinity(0))
+    threads = threads or usable_cpus()
     kind = "reference" if ol.ref_path() else "port"
     pool = ol.CpuPool(n_inst, fs=fs, impl="ref" if kind == "reference" else "oracle", cng_mode=1, echo_mode=3,
                       threads=threads)
@@ -365,7 +386,8 @@ def cpu_reference_throughput(fs, spc, n_inst, prep_calls, timed_calls, threads=N
     blocks = n_inst * timed_calls * spc / 64.0
     return {"value": blocks / secs, "unit": "blocks/s", "cores": threads, "kind": kind,
             "sample": f"{n_inst} instances x {timed_calls} steady-state 10 ms calls ({blocks:.0f} blocks) after "
-                      f"{prep_calls} warm-up calls, {threads} threads, instances statically sharded",
+                      f"{prep_calls} warm-up calls, {threads} threads (= usable CPUs: affinity {len(os.sched_getaffinity(0))}, "
+                      f"capped by the cgroup quota), instances statically sharded",
             "seconds": secs, "return_codes_or": int(acc)}
 
 
@@ -383,7 +405,7 @@ def run_reference(args):
     import oracle_lib as ol
     from webrtc_aecm_b200.synth import synth_streams
 
-    threads = len(os.sched_getaffinity(0))
+    threads = usable_cpus()
     kind = "reference" if ol.ref_path() else "port"
     # bounded sample of the workload: a slice of the batch, sized for about two million blocks in the timed region
     # (seconds of wall clock on a big host, so that starting the threads does not show) and at least 8 instances per thread
@@ -402,7 +424,8 @@ def run_reference(args):
     blocks = n_inst * K * cps * spc / 64.0
     value = blocks / secs
     cpu = {"value": value, "unit": "blocks/s", "cores": threads, "kind": kind,
-           "sample": f"{n_inst} of {B} instances x {K * cps} steady-state calls, {threads} threads"}
+           "sample": f"{n_inst} of {B} instances x {K * cps} steady-state calls, {threads} threads (= usable CPUs: "
+                     f"affinity {len(os.sched_getaffinity(0))}, capped by the cgroup quota)"}
     print(json.dumps({
         "impl": "reference", "metric": "AECM blocks/sec (64-sample, 16 kHz) across batch; bit-exact",
         "value": value, "unit": "blocks/s", "n_gpus": args.gpus, "steps": K, "warmup": W,

@@ -144,6 +144,25 @@ def ms_schedule(case, n_calls):
     return ms
 
 
+def soak_inputs(fs, n=12, seconds=120.0, seed=777):
+    """Two minutes of audio per instance for the slow state machines (store/reset decisions every >= 30 qualifying
+    blocks, VAD update halts after 1024 blocks, delay-change counters): alternating echo and stress material, per
+    instance its own echo delay and gain pattern.  -> far, near [n, T] int16"""
+    total = int(seconds * 100) * (fs // 100)
+    seg = total // 6
+    fars, nears = [], []
+    for k in range(6):
+        kind = "stress" if k % 3 == 2 else "echo"
+        f, x = synth_streams(n, seg, fs, seed=seed + k, delay_ms=(np.arange(n) * 11 + 7 * k) % 121, kind=kind)
+        fars.append(f)
+        nears.append(x)
+    far, near = np.concatenate(fars, axis=1), np.concatenate(nears, axis=1)
+    pad = total - far.shape[1]
+    if pad:
+        far, near = np.pad(far, ((0, 0), (0, pad))), np.pad(near, ((0, 0), (0, pad)))
+    return np.ascontiguousarray(far), np.ascontiguousarray(near)
+
+
 def run_kwargs(case):
     """The case's API-level parameters as keyword arguments of oracle_lib.run_streams."""
     return dict(fs=case["fs"], samples_per_call=case["spc"], cng_mode=case["cng"], echo_mode=case["echo_mode"],

@@ -148,6 +148,39 @@ def test_full_batch_4096_properties():
     b.close()
 
 
+@pytest.mark.parametrize("fs", [16000, 8000])
+def test_two_minute_soak_matches_oracle(fs):
+    """120 s of audio per instance (12 000 API calls, fused 100 per launch) against the oracle, output and final state."""
+    from cases import soak_inputs
+    from webrtc_aecm_b200 import AecmBatch
+
+    far, near = soak_inputs(fs)
+    n, total = far.shape
+    spc = fs // 100
+    ms = ((np.arange(n) * 37) % 300).astype(np.int16)
+    want, _, _ = ol.run_streams(far, near, fs=fs, impl="oracle", ms=ms, echo_mode=3)
+    b = AecmBatch(n, 0)
+    assert b.init(fs) == 0
+    out = np.zeros_like(near)
+    step = 100 * spc
+    for t0 in range(0, total, step):
+        sl = slice(t0, min(total, t0 + step))
+        rc, o, status = b.process_stream(np.ascontiguousarray(far[:, sl]), np.ascontiguousarray(near[:, sl]),
+                                         samples_per_call=spc, ms=ms)
+        assert rc == 0 and not status.any()
+        out[:, sl] = o
+    bad = np.nonzero((out != want).any(axis=1))[0]
+    assert bad.size == 0, f"instances {bad[:8]} differ, first sample {np.argmax(out[bad[0]] != want[bad[0]])}"
+    # final state of one instance, field by field
+    o = ol.OracleInstance(fs, 1, 3)
+    for c in range(total // spc):
+        o.buffer_farend(far[3, c * spc:(c + 1) * spc])
+        o.process(near[3, c * spc:(c + 1) * spc], None, int(ms[3]))
+    assert ol.compare_states(b.read_state(3), o.state()) == []
+    o.close()
+    b.close()
+
+
 def test_delay_sweep_32768_instances_sampled():
     """BASELINE configs[4] size: per-instance far-end delay 0-120 ms across 32768 instances; every 257th
     instance is checked against the oracle, all others through stream-duplication equality."""

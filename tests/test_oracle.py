@@ -139,3 +139,18 @@ def test_adversarial_cases_reach_the_wide_shift_corner():
                        echo_mode=case["echo_mode"], threads=1)
         hit += lib.oracle_debug_wide_shift_events() - before
     assert hit >= 10
+
+
+@pytest.mark.skipif(ol.ref_path() is None, reason="oracle/_ref/libaecm_ref.so not built (needs /root/reference)")
+@pytest.mark.parametrize("fs", [16000, 8000])
+def test_two_minute_soak_oracle_equals_reference(fs):
+    """120 s per instance: the slow state machines (channel store/reset, VAD update halt, delay-change counters) stay
+    bit-identical between the restatement and the unmodified reference far beyond the length of the golden cases."""
+    from cases import soak_inputs
+
+    far, near = soak_inputs(fs)
+    ms = (np.arange(far.shape[0]) * 37) % 300
+    a, ra, _ = ol.run_streams(far, near, fs=fs, impl="oracle", ms=ms, echo_mode=3)
+    b, rb, _ = ol.run_streams(far, near, fs=fs, impl="ref", ms=ms, echo_mode=3)
+    np.testing.assert_array_equal(a, b)
+    np.testing.assert_array_equal(ra, rb)
