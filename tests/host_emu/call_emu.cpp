@@ -1,0 +1,63 @@
+// call_emu.cpp -- TEST INFRASTRUCTURE.  Compiles the DEVICE code of the hot path (aecm_frame_api.cuh -> aecm_block.cuh
+// -> aecm_prims.cuh -> aecm_fft.cuh, plus aecm_init.cuh) for the host against warp_emu.h and drives one instance through
+// whole streams of 10 ms API calls exactly as aecm_call_kernel does for one warp: the record lives in ordinary memory
+// instead of shared memory, the far history and the far-end jitter ring in ordinary memory instead of HBM, the TMA
+// copies are not needed.  Everything else -- every line of arithmetic and every warp-level operation -- is the code the
+// GPU runs.  tests/test_call_path_emulated_warp.py compares the output with the oracle / golden streams.
+#define AECM_HOST_EMU 1
+#include "warp_emu.h"
+
+#include "../../webrtc_aecm_b200/csrc/aecm_frame_api.cuh"
+#include "../../webrtc_aecm_b200/csrc/aecm_init.cuh"
+
+namespace {
+
+struct Emu {
+    alignas(16) AecmInstanceState st;
+    alignas(16) WarpScratch sc;
+    uint16_t far_hist[AECM_MAX_DELAY * AECM_HIST_ROW];
+    int16_t far_ring[AECM_FAR_RING];
+};
+
+}  // namespace
+
+extern "C" {
+
+size_t emu_state_bytes(void) { return sizeof(AecmInstanceState); }
+
+// One instance, n_calls API calls of `spc` samples.  ms: per-call msInSndCardBuf [n_calls].  far_ops: per call how
+// many times BufferFarend runs before Process (0 = underrun, 1 = normal, 2 = overrun).  Returns the OR of all return
+// codes; *state_out (optional) receives the final record.
+int emu_run_stream(int fs, int cng_mode, int echo_mode, const int16_t *far, const int16_t *near_noisy, const int16_t *near_clean,
+                   int16_t *out, int n_calls, int spc, const int16_t *ms, const uint8_t *far_ops, void *state_out,
+                   long *barriers) {
+    Emu *e = new Emu();
+    memset(e, 0, sizeof(*e));
+    int acc = 0;
+    warp_emu::g_barriers = 0;
+    warp_emu::run([&](int lane) {
+        init_instance(&e->st, fs, lane);
+        __syncwarp();
+        if (lane == 0) apply_config(e->st.s, cng_mode, echo_mode);
+        __syncwarp();
+        Ctx c;
+        c.st = &e->st;
+        c.sc = &e->sc;
+        c.far_hist = e->far_hist;
+        c.far_ring = e->far_ring;
+        c.lane = lane;
+        for (int call = 0; call < n_calls; call++) {
+            const size_t o = (size_t)call * (size_t)spc;
+            int r = 0;
+            for (int rep = 0; rep < (far_ops ? far_ops[call] : 1); rep++) r |= api_buffer_farend(c, far + o, spc);
+            r |= api_process(c, true, near_noisy + o, near_clean ? near_clean + o : nullptr, out + o, spc, ms ? ms[call] : 40);
+            if (lane == 0) acc |= r;
+        }
+    });
+    if (state_out) memcpy(state_out, &e->st, sizeof(e->st));
+    if (barriers) *barriers = warp_emu::g_barriers;
+    delete e;
+    return acc;
+}
+
+}  // extern "C"

@@ -1,0 +1,97 @@
+"""CPU check of DEVICE code, whole call path: the headers the GPU kernel is made of (aecm_frame_api.cuh ->
+aecm_block.cuh -> aecm_prims.cuh -> aecm_fft.cuh, aecm_init.cuh) are compiled for the host against
+tests/host_emu/warp_emu.h (a warp = 32 cooperative fibers, warp-level operations = rendezvous points) and driven
+through whole streams of WebRtcAecm_BufferFarend / WebRtcAecm_Process calls.  Output, return codes and the final
+instance record must equal the oracle's bit for bit -- the same comparison the GPU tests make, without a GPU, so the
+CPU suite already catches an arithmetic slip in the kernel source."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+import oracle_lib as ol
+from cases import CASE_BY_NAME, CASES, far_mask, make_inputs, run_kwargs
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "..", "webrtc_aecm_b200", "csrc")
+SRC = os.path.join(HERE, "host_emu", "call_emu.cpp")
+LIB = os.path.join(HERE, "host_emu", "libcall_emu.so")
+DEPS = [SRC, os.path.join(HERE, "host_emu", "warp_emu.h")] + [os.path.join(CSRC, f) for f in (
+    "aecm_frame_api.cuh", "aecm_block.cuh", "aecm_prims.cuh", "aecm_fft.cuh", "aecm_init.cuh", "aecm_state.h", "aecm_tables.h")]
+
+
+@pytest.fixture(scope="module")
+def emu():
+    if not os.path.exists(LIB) or any(os.path.getmtime(d) > os.path.getmtime(LIB) for d in DEPS):
+        subprocess.check_call(["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-I", os.path.join(HERE, "..", "include"), "-o", LIB, SRC])
+    lib = C.CDLL(LIB)
+    lib.emu_state_bytes.restype = C.c_size_t
+    lib.emu_run_stream.restype = C.c_int
+    return lib
+
+
+def emu_run(lib, case, far, near, clean, ms, instance, want_state=False):
+    """One instance of a case through the emulated warp -> (out, or-of-return-codes, state bytes or None)."""
+    spc = case["spc"]
+    calls = far.shape[1] // spc
+    if ms is None:
+        ms_calls = np.full(calls, 40, dtype=np.int16)
+    elif np.ndim(ms) == 2:
+        ms_calls = np.ascontiguousarray(ms[instance], dtype=np.int16)
+    else:
+        ms_calls = np.full(calls, int(np.resize(ms, far.shape[0])[instance]), dtype=np.int16)
+    ops = np.ones(calls, dtype=np.uint8)
+    if case["skip_far_every"]:
+        ops[far_mask(case, calls)[:, 0] == 0] = 0
+    k = case["extra_far_every"]
+    if k:
+        ops[(np.arange(calls) % k == k - 1) & (ops > 0)] = 2
+    f, x = np.ascontiguousarray(far[instance]), np.ascontiguousarray(near[instance])
+    cl = None if clean is None else np.ascontiguousarray(clean[instance])
+    out = np.zeros_like(x)
+    state = np.zeros(lib.emu_state_bytes(), dtype=np.uint8) if want_state else None
+    nbar = C.c_long(0)
+    acc = lib.emu_run_stream(case["fs"], case["cng"], case["echo_mode"], f.ctypes.data_as(C.c_void_p), x.ctypes.data_as(C.c_void_p),
+                             None if cl is None else cl.ctypes.data_as(C.c_void_p), out.ctypes.data_as(C.c_void_p), calls, spc,
+                             ms_calls.ctypes.data_as(C.c_void_p), ops.ctypes.data_as(C.c_void_p),
+                             None if state is None else state.ctypes.data_as(C.c_void_p), C.byref(nbar))
+    return out, acc, state
+
+
+# every case family; two instances each (the GPU suite runs all instances of all cases)
+EMU_CASES = [c["name"] for c in CASES]
+
+
+@pytest.mark.parametrize("name", EMU_CASES)
+def test_device_code_on_emulated_warp_matches_oracle(emu, name):
+    case = CASE_BY_NAME[name]
+    far, near, clean, ms = make_inputs(case)
+    want, ret, _ = ol.run_streams(far, near, impl="oracle", clean=clean, ms=ms, **run_kwargs(case))
+    n = far.shape[0]
+    for instance in sorted({1 % n, n - 1}):
+        out, acc, _ = emu_run(emu, case, far, near, clean, ms, instance)
+        bad = np.nonzero(out != want[instance])[0]
+        assert bad.size == 0, f"instance {instance}: first differing sample {bad[0]} (call {bad[0] // case['spc']})"
+        assert (acc != 0) == (ret[instance] != 0)
+
+
+def test_final_record_equals_oracle_state_field_by_field(emu):
+    """The record the emulated warp leaves behind is the device's AecmInstanceState: compare it with the oracle's state
+    through the same field map the GPU state test uses."""
+    from webrtc_aecm_b200 import api
+
+    case = CASE_BY_NAME["16k_stress"]
+    far, near, clean, ms = make_inputs(case)
+    spc, calls = case["spc"], 300
+    far, near = far[:, :calls * spc], near[:, :calls * spc]
+    out, acc, state = emu_run(emu, case, far, near, None, None, 2, want_state=True)
+    o = ol.OracleInstance(case["fs"], case["cng"], case["echo_mode"])
+    for c in range(calls):
+        o.buffer_farend(far[2, c * spc:(c + 1) * spc])
+        rc, w = o.process(near[2, c * spc:(c + 1) * spc], None, 40)
+        np.testing.assert_array_equal(out[c * spc:(c + 1) * spc], w)
+    dev = api.InstanceState.from_buffer_copy(state.tobytes())
+    assert ol.compare_states(dev, o.state()) == []
+    o.close()

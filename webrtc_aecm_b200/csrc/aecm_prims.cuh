@@ -3,7 +3,9 @@
 #ifndef AECM_PRIMS_CUH_
 #define AECM_PRIMS_CUH_
 
+#ifndef AECM_HOST_EMU  // tests/host_emu supplies the CUDA vocabulary itself
 #include <cuda_runtime.h>
+#endif
 #include <stdint.h>
 
 #include "aecm_fft.cuh"
@@ -125,6 +127,9 @@ struct Ctx {
 
 // wait for a bulk load (phase 0 of its mbarrier); returns at once when the data already arrived
 __device__ __forceinline__ void mbar_wait(uint64_t *bar) {
+#ifdef AECM_HOST_EMU  // tests/host_emu: the record is already in place
+    (void)bar;
+#else
     asm volatile(
         "{\n"
         ".reg .pred p;\n"
@@ -135,6 +140,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar) {
         "DONE_RECORD:\n"
         "}\n" ::"r"((uint32_t)__cvta_generic_to_shared(bar))
         : "memory");
+#endif
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -145,9 +151,14 @@ __device__ __forceinline__ int norm_w32(int a) { return a == 0 ? 0 : __clz(a < 0
 __device__ __forceinline__ int norm_u32(unsigned a) { return a == 0 ? 0 : __clz((int)a); }          // spl_inl.h:101
 __device__ __forceinline__ int norm_w16(int a) { return a == 0 ? 0 : __clz(a < 0 ? ~a : a) - 17; } // spl_inl.h:107
 __device__ __forceinline__ int add_sat32(int a, int b) {  // spl_inl.h:70-82
+#ifdef AECM_HOST_EMU
+    const long long w = (long long)a + b;
+    return (int)(w > 2147483647LL ? 2147483647LL : (w < -2147483648LL ? -2147483648LL : w));
+#else
     int r;
     asm("add.sat.s32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b));
     return r;
+#endif
 }
 __device__ __forceinline__ int sat16(int v) { return max(-32768, min(32767, v)); }  // spl_inl.h:59-68
 __device__ __forceinline__ uint32_t pack16(int lo, int hi) { return __byte_perm((uint32_t)lo, (uint32_t)hi, 0x5410); }
@@ -168,7 +179,11 @@ __device__ __forceinline__ uint32_t shift_u32(uint32_t x, int c) { return c >= 0
 // aecm_sqrt_selftest_kernel below sweeps all 2^31 arguments on the device (tests/test_gpu_parity.py).
 __device__ __forceinline__ int sqrt_floor(int v) {
     float f;
+#ifdef AECM_HOST_EMU  // any estimate within +-1 of the root will do (see above): the host's sqrtf
+    f = sqrtf((float)(uint32_t)v);
+#else
     asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(f) : "f"(__uint2float_rn((uint32_t)v)));
+#endif
     uint32_t r = (uint32_t)__float2int_rz(f);
     if (r * r > (uint32_t)v) r--;
     if ((r + 1) * (r + 1) <= (uint32_t)v) r++;
