@@ -12,6 +12,11 @@
  * every instance alike; AECM_UNSPECIFIED_ERROR when CUDA failed (AecmB200_LastError() has the text).
  * Per-instance return codes (0, AECM_UNINITIALIZED_ERROR, AECM_BAD_PARAMETER_WARNING, ...) are delivered
  * in the optional status[] array, one int32 per instance of the range.
+ *
+ * Threads: a batch (and a group) takes one caller at a time -- there is no locking inside; different batches may be
+ * driven from different threads, also on the same GPU.  The ten WebRtcAecm_* symbols of echo_control_mobile.h ARE
+ * safe to call concurrently for different instances, as with the reference (they serialise and combine their calls
+ * internally).  There is no CPU implementation behind any of this: without a CUDA device Create returns NULL.
  */
 #ifndef AECM_B200_H_
 #define AECM_B200_H_
