@@ -41,10 +41,13 @@ typedef struct {
     int spc;          /* samples per 10 ms call, 0 = rate not supported */
     int64_t n_calls;  /* whole 10 ms frames in the near file */
     int skip;         /* unreadable or not mono: no output */
+    int failed;       /* unreadable input or unwritable output */
+    int unsupported;  /* rate the canceller rejects: written back unchanged */
+    char msg[2][320]; /* what the reader / writer has to say about this pair (printed in input order) */
 } Pair;
 
 typedef struct {
-    int echo_mode, cng, ms, chunk_calls, quiet, passthrough, n_devices;
+    int echo_mode, cng, ms, chunk_calls, quiet, passthrough, n_devices, io_threads;
     int devices[64];
     const char *suffix;
 } Options;
@@ -278,6 +281,80 @@ done:
     return NULL;
 }
 
+/* ------------------------------------------------------------------------------------------------------------------
+ * file I/O on a few threads: the pairs are independent, and with thousands of small files the open/read/close round
+ * trips dominate the run otherwise
+ * ---------------------------------------------------------------------------------------------------------------- */
+typedef struct {
+    Pair *pairs;
+    int n, next, quiet, writing;
+    pthread_mutex_t lock;
+} IoJob;
+
+static void read_pair(Pair *p, int quiet) {
+    char why[128] = "";
+    uint32_t far_rate;
+    int ch_near, ch_far;
+    p->near = wav_read_mono16(p->near_path, &p->rate, &p->n_near, &ch_near, why, sizeof(why));
+    if (!p->near) {
+        if (ch_near > 1) snprintf(p->msg[0], sizeof(p->msg[0]), "skipped (near has %d channels, mono only): %.200s\n", ch_near, p->near_path);
+        else { snprintf(p->msg[0], sizeof(p->msg[0]), "error: %.200s: %s\n", p->near_path, why); p->failed = 1; }
+        p->skip = 1;
+        return;
+    }
+    p->far = wav_read_mono16(p->far_path, &far_rate, &p->n_far, &ch_far, why, sizeof(why));
+    if (!p->far) {
+        if (ch_far > 1) snprintf(p->msg[0], sizeof(p->msg[0]), "skipped (far has %d channels, mono only): %.200s\n", ch_far, p->far_path);
+        else { snprintf(p->msg[0], sizeof(p->msg[0]), "error: %.200s: %s\n", p->far_path, why); p->failed = 1; }
+        p->skip = 1;
+        return;
+    }
+    if ((p->rate == 8000 || p->rate == 16000) && p->n_near > 0) { /* WebRtcAecm_Init, echo_control_mobile.cc:150-152 */
+        p->spc = (int)(p->rate / 100);
+        p->n_calls = (int64_t)(p->n_near / (uint64_t)p->spc);
+    } else {
+        p->unsupported = 1;
+        if (!quiet) snprintf(p->msg[0], sizeof(p->msg[0]), "not processed (rate %u Hz): %.200s is written back unchanged\n", p->rate, p->near_path);
+    }
+    if (p->n_far < (uint64_t)p->n_calls * (uint64_t)p->spc && !quiet)
+        snprintf(p->msg[0], sizeof(p->msg[0]), "note: %.200s is shorter than its near file; padded with silence\n", p->far_path);
+}
+
+static void *io_worker(void *arg) {
+    IoJob *j = (IoJob *)arg;
+    for (;;) {
+        int i;
+        Pair *p;
+        pthread_mutex_lock(&j->lock);
+        i = j->next++;
+        pthread_mutex_unlock(&j->lock);
+        if (i >= j->n) return NULL;
+        p = &j->pairs[i];
+        if (!j->writing) {
+            read_pair(p, j->quiet);
+        } else if (!p->skip && wav_write_mono16(p->out_path, p->near, p->n_near, p->rate)) {
+            snprintf(p->msg[1], sizeof(p->msg[1]), "error: cannot write %.200s\n", p->out_path);
+            p->failed = 1;
+        }
+    }
+}
+
+static void run_io(Pair *pairs, int n, int threads, int quiet, int writing) {
+    IoJob j;
+    pthread_t th[64];
+    int t;
+    j.pairs = pairs; j.n = n; j.next = 0; j.quiet = quiet; j.writing = writing;
+    pthread_mutex_init(&j.lock, NULL);
+    if (threads > n) threads = n;
+    if (threads > 64) threads = 64;
+    for (t = 1; t < threads; t++) pthread_create(&th[t], NULL, io_worker, &j);
+    io_worker(&j);
+    for (t = 1; t < threads; t++) pthread_join(th[t], NULL);
+    pthread_mutex_destroy(&j.lock);
+    for (t = 0; t < n; t++)
+        if (pairs[t].msg[writing][0]) fputs(pairs[t].msg[writing], stderr); /* in input order */
+}
+
 static int by_calls_desc(const void *x, const void *y) {
     const Pair *a = *(Pair *const *)x, *b = *(Pair *const *)y;
     if (a->n_calls != b->n_calls) return a->n_calls < b->n_calls ? 1 : -1;
@@ -293,7 +370,7 @@ static void usage(void) {
             "  --ms MS            msInSndCardBuf for every call (default 40, as main.cc)\n"
             "  --gpus N | --devices a,b,..   CUDA devices to spread the pairs over (default: device 0)\n"
             "  --chunk-calls K    10 ms calls per kernel launch (default 100)\n"
-            "  --suffix S         output suffix (default _out)     -q  quiet\n"
+            "  --suffix S         output suffix (default _out)     -q  quiet     --io-threads T  file readers/writers (default 8)\n"
             "  --passthrough      I/O self-test: read, do not process, write (no GPU needed)\n");
 }
 
@@ -318,7 +395,7 @@ int main(int argc, char **argv) {
     int launches = 0;
     double audio_s = 0;
     memset(&o, 0, sizeof(o));
-    o.echo_mode = 1; o.cng = 1; o.ms = 40; o.chunk_calls = 100; o.suffix = "_out"; o.n_devices = 1; o.devices[0] = 0;
+    o.echo_mode = 1; o.cng = 1; o.ms = 40; o.chunk_calls = 100; o.suffix = "_out"; o.n_devices = 1; o.devices[0] = 0; o.io_threads = 8;
     for (i = 1; i < argc; i++) {
         const char *a = argv[i];
         if (!strcmp(a, "--echo-mode") && i + 1 < argc) o.echo_mode = atoi(argv[++i]);
@@ -326,6 +403,7 @@ int main(int argc, char **argv) {
         else if (!strcmp(a, "--ms") && i + 1 < argc) o.ms = atoi(argv[++i]);
         else if (!strcmp(a, "--chunk-calls") && i + 1 < argc) o.chunk_calls = atoi(argv[++i]);
         else if (!strcmp(a, "--suffix") && i + 1 < argc) o.suffix = argv[++i];
+        else if (!strcmp(a, "--io-threads") && i + 1 < argc) o.io_threads = atoi(argv[++i]);
         else if (!strcmp(a, "--list") && i + 1 < argc && n_lists < 64) lists[n_lists++] = argv[++i];
         else if (!strcmp(a, "--gpus") && i + 1 < argc) {
             o.n_devices = atoi(argv[++i]);
@@ -344,7 +422,7 @@ int main(int argc, char **argv) {
         else if (i + 1 < argc) { add_pair(&pairs, &n, &cap, argv[i], argv[i + 1], NULL, o.suffix); i++; }
         else { fprintf(stderr, "far file %s has no near file\n", a); return 2; }
     }
-    if (o.echo_mode < 0 || o.echo_mode > 4 || (o.cng != 0 && o.cng != 1) || o.chunk_calls < 1 || o.ms < 0 || o.ms > 500) { usage(); return 2; }
+    if (o.echo_mode < 0 || o.echo_mode > 4 || (o.cng != 0 && o.cng != 1) || o.chunk_calls < 1 || o.ms < 0 || o.ms > 500 || o.io_threads < 1) { usage(); return 2; }
     for (i = 0; i < n_lists; i++) {
         FILE *f = fopen(lists[i], "r");
         char line[4096];
@@ -361,34 +439,10 @@ int main(int argc, char **argv) {
     if (!o.passthrough && AecmB200_DeviceCount() < 1) { fprintf(stderr, "aecm_wav_batch: no CUDA device; this tool has no CPU path\n"); return 3; }
 
     t0 = now_s();
+    run_io(pairs, n, o.io_threads, o.quiet, 0);
     for (i = 0; i < n; i++) {
-        Pair *p = &pairs[i];
-        char why[128] = "";
-        uint32_t far_rate;
-        int ch_near, ch_far;
-        p->near = wav_read_mono16(p->near_path, &p->rate, &p->n_near, &ch_near, why, sizeof(why));
-        if (!p->near) {
-            if (ch_near > 1) fprintf(stderr, "skipped (near has %d channels, mono only): %s\n", ch_near, p->near_path);
-            else { fprintf(stderr, "error: %s: %s\n", p->near_path, why); bad++; }
-            p->skip = 1;
-            continue;
-        }
-        p->far = wav_read_mono16(p->far_path, &far_rate, &p->n_far, &ch_far, why, sizeof(why));
-        if (!p->far) {
-            if (ch_far > 1) fprintf(stderr, "skipped (far has %d channels, mono only): %s\n", ch_far, p->far_path);
-            else { fprintf(stderr, "error: %s: %s\n", p->far_path, why); bad++; }
-            p->skip = 1;
-            continue;
-        }
-        if ((p->rate == 8000 || p->rate == 16000) && p->n_near > 0) { /* WebRtcAecm_Init, echo_control_mobile.cc:150-152 */
-            p->spc = (int)(p->rate / 100);
-            p->n_calls = (int64_t)(p->n_near / (uint64_t)p->spc);
-        } else {
-            unsupported++;
-            if (!o.quiet) fprintf(stderr, "not processed (rate %u Hz): %s is written back unchanged\n", p->rate, p->near_path);
-        }
-        if (p->n_far < (uint64_t)p->n_calls * (uint64_t)p->spc && !o.quiet)
-            fprintf(stderr, "note: %s is shorter than its near file; padded with silence\n", p->far_path);
+        bad += pairs[i].failed;
+        unsupported += pairs[i].unsupported;
     }
     t_read = now_s() - t0;
 
@@ -428,10 +482,12 @@ int main(int argc, char **argv) {
     t_proc = now_s() - t0;
 
     t0 = now_s();
+    for (i = 0; i < n; i++) pairs[i].failed = 0;
+    run_io(pairs, n, o.io_threads, o.quiet, 1);
     for (i = 0; i < n; i++) {
         Pair *p = &pairs[i];
         if (p->skip) { skipped++; continue; }
-        if (wav_write_mono16(p->out_path, p->near, p->n_near, p->rate)) { fprintf(stderr, "error: cannot write %s\n", p->out_path); bad++; continue; }
+        if (p->failed) { bad++; continue; }
         written++;
         if (p->spc) audio_s += (double)p->n_calls / 100.0;
     }
