@@ -32,7 +32,7 @@ def emu():
     return lib
 
 
-def emu_run(lib, case, far, near, clean, ms, instance, want_state=False):
+def emu_run(lib, case, far, near, clean, ms, instance, want_state=False, misalign=False):
     """One instance of a case through the emulated warp -> (out, or-of-return-codes, state bytes or None)."""
     spc = case["spc"]
     calls = far.shape[1] // spc
@@ -48,9 +48,17 @@ def emu_run(lib, case, far, near, clean, ms, instance, want_state=False):
     k = case["extra_far_every"]
     if k:
         ops[(np.arange(calls) % k == k - 1) & (ops > 0)] = 2
-    f, x = np.ascontiguousarray(far[instance]), np.ascontiguousarray(near[instance])
-    cl = None if clean is None else np.ascontiguousarray(clean[instance])
-    out = np.zeros_like(x)
+    def plane(a):  # misalign: the first sample sits at an odd int16 position, so 32-bit movers cannot be used
+        if not misalign:
+            return np.ascontiguousarray(a)
+        buf = np.zeros(a.size + 2, dtype=np.int16)
+        off = 1 if buf.ctypes.data % 4 == 0 else 2
+        buf[off:off + a.size] = a
+        return buf[off:off + a.size]
+
+    f, x = plane(far[instance]), plane(near[instance])
+    cl = None if clean is None else plane(clean[instance])
+    out = plane(np.zeros_like(near[instance]))
     state = np.zeros(lib.emu_state_bytes(), dtype=np.uint8) if want_state else None
     nbar = C.c_long(0)
     acc = lib.emu_run_stream(case["fs"], case["cng"], case["echo_mode"], f.ctypes.data_as(C.c_void_p), x.ctypes.data_as(C.c_void_p),
@@ -75,6 +83,17 @@ def test_device_code_on_emulated_warp_matches_oracle(emu, name):
         bad = np.nonzero(out != want[instance])[0]
         assert bad.size == 0, f"instance {instance}: first differing sample {bad[0]} (call {bad[0] // case['spc']})"
         assert (acc != 0) == (ret[instance] != 0)
+
+
+@pytest.mark.parametrize("name", ["16k_ms_mix", "8k_far_underrun_ms_mix", "16k_clean_path"])
+def test_planes_that_are_not_32_bit_aligned(emu, name):
+    """Audio rows at odd int16 offsets (odd row strides, sub-ranges): the sample movers fall back from 32-bit words to
+    16-bit accesses and must produce the same stream."""
+    case = CASE_BY_NAME[name]
+    far, near, clean, ms = make_inputs(case)
+    want, _, _ = ol.run_streams(far, near, impl="oracle", clean=clean, ms=ms, **run_kwargs(case))
+    out, _, _ = emu_run(emu, case, far, near, clean, ms, 0, misalign=True)
+    np.testing.assert_array_equal(out, want[0])
 
 
 def test_final_record_equals_oracle_state_field_by_field(emu):

@@ -305,6 +305,39 @@ def test_pipelined_submit_wait_equals_synchronous(adjacent, all_slots):
     b.close()
 
 
+def test_device_planes_at_odd_sample_offsets_and_strides():
+    """AecmB200_ProcessStreamDevice with rows that start at odd int16 positions (odd row stride, offset 1): the kernel's
+    32-bit sample movers must fall back to 16-bit accesses and still produce the oracle's stream."""
+    import torch
+
+    from webrtc_aecm_b200 import AecmBatch
+
+    fs, spc, n, calls = 16000, 160, 9, 40
+    far, near = synth_streams(n, calls * spc, fs, seed=4321, delay_ms=np.arange(n) * 9)
+    clean = np.ascontiguousarray(near[:, ::-1] // 2)
+    want, _, _ = ol.run_streams(far, near, fs=fs, impl="oracle", clean=clean)
+    stride = calls * spc + 3  # odd: every second row starts on an odd sample
+    dev = torch.device("cuda", 0)
+
+    def plane(a):
+        t = torch.zeros((n, stride), dtype=torch.int16, device=dev)
+        t[:, 1:1 + a.shape[1]] = torch.from_numpy(a).to(dev)
+        return t
+
+    d_far, d_near, d_clean, d_out = plane(far), plane(near), plane(clean), plane(np.zeros_like(near))
+    b = AecmBatch(n, 0)
+    b.adopt_cuda_stream(torch.cuda.current_stream().cuda_stream)
+    assert b.init(fs) == 0
+    for c0 in range(0, calls, 8):
+        rc = b.process_stream_device(d_far, d_near, d_clean, d_out, row_stride=stride, samples_per_call=spc, n_calls=min(8, calls - c0),
+                                     sample_offset=1 + c0 * spc)
+        assert rc == 0
+    b.synchronize()
+    got = d_out[:, 1:1 + calls * spc].cpu().numpy()
+    np.testing.assert_array_equal(got, want)
+    b.close()
+
+
 def test_instance_index_scatters_rows_over_the_batch():
     """AecmB200StreamArgs.instanceIndex: plane row r works on instance instanceIndex[r].  A permuted subset of a batch,
     driven through host planes, must equal the oracle per stream while the untouched instances stay untouched."""

@@ -278,7 +278,7 @@ __device__ __forceinline__ int api_process(const Ctx &c, bool live, const int16_
         }
     }
     for (int i = 0; i < n_frames; i++) {  // :358-397
-        int far_idx = -1;
+        int far_idx = -2;  // "replay farend_old" (even, so that the word-wide mover still applies)
         if (processing) {  // wrapper bookkeeping of this frame on register copies, committed before the frame is processed
             DelayRegs d;
             d.far_rd = S.far_rd; d.far_cnt = S.far_cnt;
