@@ -1,5 +1,6 @@
 // fft_emu.cpp -- TEST INFRASTRUCTURE.  Executes aecm_fft.cuh on an emulated warp and exposes C entry points
 // with the same contract as the oracle's oracle_real_fft128_forward / _inverse, so tests can compare them.
+#define AECM_HOST_EMU 1
 #include "warp_emu.h"
 
 #include <string.h>

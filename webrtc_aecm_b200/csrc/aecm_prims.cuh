@@ -212,8 +212,8 @@ __device__ __forceinline__ int asym_filt(int old_v, int in, int step_pos, int st
 }
 
 __device__ __forceinline__ int wrap_add(int base, int k, int cap) {  // (base + k) mod cap for 0 <= base,k < cap
-    const int v = base + k;
-    return v >= cap ? v - cap : v;
+    const unsigned v = (unsigned)(base + k);
+    return (int)min(v, v - (unsigned)cap);  // v - cap wraps to a huge value exactly when v < cap
 }
 
 }  // namespace
