@@ -233,3 +233,41 @@ def test_deferred_far_end_keeps_the_callers_order():
             both_process(160, 40)
     L.WebRtcAecm_Free(h)
     o.close()
+
+
+def test_live_config_and_echo_path_changes_mid_stream():
+    """WebRtcAecm_set_config and WebRtcAecm_InitEchoPath on a running instance: every later call must
+    follow the oracle that received the same control calls at the same points."""
+    from webrtc_aecm_b200 import api
+
+    L = api.scalar_api()
+    lib = ol.oracle()
+    fs, spc, calls = 8000, 80, 260
+    far, near = synth_streams(1, calls * spc, fs, seed=2024, delay_ms=35)
+    h = L.WebRtcAecm_Create()
+    o = ol.OracleInstance(fs, 1, 3)
+    assert L.WebRtcAecm_Init(h, fs) == 0
+    path = (np.arange(65) * 53 % 3000 + 200).astype(np.int16)
+    schedule = {40: (0, 1), 90: (1, 4), 91: (1, 0), 170: (0, 3)}  # call -> (cngMode, echoMode)
+    for c in range(calls):
+        if c in schedule:
+            cng, mode = schedule[c]
+            assert L.WebRtcAecm_set_config(h, api.AecmConfig(cng, mode)) == 0
+            assert lib.oracle_aecm_set_config(o.h, cng, mode) == 0
+        if c == 130:  # import a channel estimate in the middle of the call
+            assert L.WebRtcAecm_InitEchoPath(h, P(path), 130) == 0
+            assert lib.oracle_aecm_init_echo_path(o.h, path.ctypes.data_as(C.c_void_p), 130) == 0
+        f = np.ascontiguousarray(far[0, c * spc:(c + 1) * spc])
+        x = np.ascontiguousarray(near[0, c * spc:(c + 1) * spc])
+        out = np.zeros_like(x)
+        assert L.WebRtcAecm_BufferFarend(h, P(f), spc) == 0 and o.buffer_farend(f) == 0
+        rc = L.WebRtcAecm_Process(h, P(x), None, P(out), spc, 30)
+        want_rc, want = o.process(x, None, 30)
+        assert rc == want_rc
+        np.testing.assert_array_equal(out, want, err_msg=f"call {c}")
+    got, wantp = np.zeros(65, np.int16), np.zeros(65, np.int16)
+    assert L.WebRtcAecm_GetEchoPath(h, P(got), 130) == 0
+    assert lib.oracle_aecm_get_echo_path(o.h, wantp.ctypes.data_as(C.c_void_p), 130) == 0
+    np.testing.assert_array_equal(got, wantp)
+    L.WebRtcAecm_Free(h)
+    o.close()

@@ -154,3 +154,53 @@ def test_two_minute_soak_oracle_equals_reference(fs):
     b, rb, _ = ol.run_streams(far, near, fs=fs, impl="ref", ms=ms, echo_mode=3)
     np.testing.assert_array_equal(a, b)
     np.testing.assert_array_equal(ra, rb)
+
+
+@pytest.mark.skipif(ol.ref_path() is None, reason="oracle/_ref/libaecm_ref.so not built (needs /root/reference)")
+def test_live_config_and_echo_path_changes_oracle_equals_reference():
+    """Control calls on a running instance (set_config with every mode, InitEchoPath, a second Init): the restatement
+    and the reference library, driven call by call through their C APIs, stay bit-identical."""
+    from webrtc_aecm_b200.synth import synth_streams
+
+    class Cfg(C.Structure):
+        _fields_ = [("cngMode", C.c_int16), ("echoMode", C.c_int16)]
+
+    ref = C.CDLL(ol.ref_path())
+    ref.WebRtcAecm_Create.restype = C.c_void_p
+    for name, args in (("WebRtcAecm_Init", [C.c_void_p, C.c_int32]), ("WebRtcAecm_Free", [C.c_void_p]),
+                       ("WebRtcAecm_BufferFarend", [C.c_void_p, C.c_void_p, C.c_size_t]),
+                       ("WebRtcAecm_Process", [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_int16]),
+                       ("WebRtcAecm_set_config", [C.c_void_p, Cfg]), ("WebRtcAecm_InitEchoPath", [C.c_void_p, C.c_void_p, C.c_size_t]),
+                       ("WebRtcAecm_GetEchoPath", [C.c_void_p, C.c_void_p, C.c_size_t])):
+        getattr(ref, name).argtypes = args
+    lib = ol.oracle()
+    fs, spc, calls = 8000, 80, 400
+    far, near = synth_streams(1, calls * spc, fs, seed=2024, delay_ms=35)
+    r = ref.WebRtcAecm_Create()
+    o = ol.OracleInstance(fs, 1, 3)
+    assert ref.WebRtcAecm_Init(r, fs) == 0
+    path = (np.arange(65) * 53 % 3000 + 200).astype(np.int16)
+    schedule = {40: (0, 1), 90: (1, 4), 91: (1, 0), 170: (0, 3), 300: (1, 2)}
+    for c in range(calls):
+        if c in schedule:
+            cng, mode = schedule[c]
+            assert ref.WebRtcAecm_set_config(r, Cfg(cng, mode)) == lib.oracle_aecm_set_config(o.h, cng, mode) == 0
+        if c == 130:
+            assert ref.WebRtcAecm_InitEchoPath(r, path.ctypes.data_as(C.c_void_p), 130) == 0
+            assert lib.oracle_aecm_init_echo_path(o.h, path.ctypes.data_as(C.c_void_p), 130) == 0
+        if c == 250:  # re-Init in the middle of a stream
+            assert ref.WebRtcAecm_Init(r, fs) == lib.oracle_aecm_init(o.h, fs) == 0
+        f = np.ascontiguousarray(far[0, c * spc:(c + 1) * spc])
+        x = np.ascontiguousarray(near[0, c * spc:(c + 1) * spc])
+        out = np.zeros_like(x)
+        assert ref.WebRtcAecm_BufferFarend(r, f.ctypes.data_as(C.c_void_p), spc) == o.buffer_farend(f) == 0
+        rc = ref.WebRtcAecm_Process(r, x.ctypes.data_as(C.c_void_p), None, out.ctypes.data_as(C.c_void_p), spc, 30)
+        want_rc, want = o.process(x, None, 30)
+        assert rc == want_rc
+        np.testing.assert_array_equal(out, want, err_msg=f"call {c}")
+    a, b = np.zeros(65, np.int16), np.zeros(65, np.int16)
+    assert ref.WebRtcAecm_GetEchoPath(r, a.ctypes.data_as(C.c_void_p), 130) == 0
+    assert lib.oracle_aecm_get_echo_path(o.h, b.ctypes.data_as(C.c_void_p), 130) == 0
+    np.testing.assert_array_equal(a, b)
+    ref.WebRtcAecm_Free(r)
+    o.close()
