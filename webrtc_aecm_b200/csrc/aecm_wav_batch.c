@@ -187,25 +187,52 @@ static int collect(Shard *s, AecmB200Batch *b, int slot, const int32_t *status, 
     return 0;
 }
 
-/* copy the chunk [t, t + calls) of every live row into (fill != 0) or out of the slot's pinned staging planes */
-static void stage_chunk(Shard *s, int live, int64_t t, int calls, int16_t *far, int16_t *near, const int16_t *out, int fill) {
-    const size_t spc = (size_t)s->spc, width = (size_t)calls * spc;
+/* copy the chunk [t, t + calls) of the live rows [i0, i1) into (fill != 0) or out of the slot's pinned staging planes */
+typedef struct {
+    Shard *s;
+    int i0, i1, calls, fill;
+    int64_t t;
+    int16_t *far, *near;
+    const int16_t *out;
+} StageJob;
+
+static void *stage_rows(void *arg) {
+    const StageJob *j = (const StageJob *)arg;
+    const size_t spc = (size_t)j->s->spc, width = (size_t)j->calls * spc;
     int i;
-    for (i = 0; i < live; i++) {
-        Pair *p = s->pairs[i];
-        const int64_t left = p->n_calls - t; /* > 0 for a live row */
-        const size_t have = (size_t)(left < calls ? left : calls) * spc, at = (size_t)t * spc;
-        if (fill) {
+    for (i = j->i0; i < j->i1; i++) {
+        Pair *p = j->s->pairs[i];
+        const int64_t left = p->n_calls - j->t; /* > 0 for a live row */
+        const size_t have = (size_t)(left < j->calls ? left : j->calls) * spc, at = (size_t)j->t * spc;
+        if (j->fill) {
             size_t have_far = p->n_far > at ? (size_t)(p->n_far - at) : 0; /* a short far file is continued with silence */
             if (have_far > have) have_far = have;
-            memcpy(far + i * width, p->far + at, have_far * 2);
-            memset(far + i * width + have_far, 0, (width - have_far) * 2);
-            memcpy(near + i * width, p->near + at, have * 2);
-            memset(near + i * width + have, 0, (width - have) * 2); /* a row that ends inside the chunk runs on into silence */
+            memcpy(j->far + i * width, p->far + at, have_far * 2);
+            memset(j->far + i * width + have_far, 0, (width - have_far) * 2);
+            memcpy(j->near + i * width, p->near + at, have * 2);
+            memset(j->near + i * width + have, 0, (width - have) * 2); /* a row that ends inside the chunk runs on into silence */
         } else {
-            memcpy(p->near + at, out + i * width, have * 2); /* main.cc:141 */
+            memcpy(p->near + at, j->out + i * width, have * 2); /* main.cc:141 */
         }
     }
+    return NULL;
+}
+
+/* the rows are independent: a few threads move them (a chunk of 1 000 pairs is tens of megabytes each way) */
+static void stage_chunk(Shard *s, int live, int64_t t, int calls, int16_t *far, int16_t *near, const int16_t *out, int fill) {
+    StageJob job[16];
+    pthread_t th[16];
+    int T = s->opt->io_threads, k;
+    if (T > 16) T = 16;
+    if (T > live / 64 + 1) T = live / 64 + 1; /* not worth a thread below 64 rows */
+    for (k = 0; k < T; k++) {
+        job[k].s = s; job[k].calls = calls; job[k].fill = fill; job[k].t = t; job[k].far = far; job[k].near = near; job[k].out = out;
+        job[k].i0 = (int)((int64_t)live * k / T);
+        job[k].i1 = (int)((int64_t)live * (k + 1) / T);
+    }
+    for (k = 1; k < T; k++) pthread_create(&th[k], NULL, stage_rows, &job[k]);
+    stage_rows(&job[0]);
+    for (k = 1; k < T; k++) pthread_join(th[k], NULL);
 }
 
 static void *run_shard(void *arg) {
