@@ -1,12 +1,13 @@
 /*
  * aecm_oracle.h -- TEST INFRASTRUCTURE.  CPU restatement (plain C99) of the AECM hot path of
  * cpuimage/WebRTC_AECM, used only as the checker by tests/, __graft_entry__.smoke() and the
- * cpu_baseline / --impl reference legs of bench.py.  Nothing in the product (webrtc_aecm_b200/) may
- * include, link or call this file.
+ * cpu_baseline / --impl reference legs of bench.py (plus the developer utilities under tools/ that generate the
+ * golden fixtures and coverage reports).  Nothing in the product (webrtc_aecm_b200/, include/) may include, link or
+ * call this file (tests/test_abi.py checks that).
  *
  * Parity status: PINNED.  The reference ships no golden vectors or tests, so the
  * oracle is pinned against the reference itself: oracle/Makefile compiles the unmodified reference
- * sources into oracle/_ref/libaecm_ref.so, and tests/test_oracle_vs_ref.py requires bit-identical
+ * sources into oracle/_ref/libaecm_ref.so, and tests/test_oracle.py requires bit-identical
  * int16 output (and identical return codes) between this restatement and that library on every
  * stream family of SURVEY.md section 8(c); tests/golden/ holds vectors generated from the reference
  * library (script committed) for the GPU box, where /root/reference does not exist.
