@@ -3,6 +3,8 @@ import ctypes
 import os
 import re
 
+import pytest
+
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
@@ -66,3 +68,28 @@ def test_product_does_not_reference_the_oracle():
         if re.search(r"oracle", open(os.path.join(ROOT, f)).read()):
             bad.append(f)
     assert not bad, bad
+
+
+def test_built_kernel_keeps_its_launch_shape_and_hardware_paths():
+    """Static checks on the built sm_100a code (cuobjdump, no GPU): the hot kernel still fits 28 warps per SM (<= 72
+    registers, nothing spilled to local memory), moves the instance record with the bulk-copy (TMA) unit both ways
+    (UBLKCP + mbarrier SYNCS), uses the hardware square-root estimate and warp-wide redux -- so an edit that silently
+    costs the residency or falls back to a slower path fails here before it reaches a GPU."""
+    import re
+    import shutil
+    import subprocess
+
+    if not shutil.which("cuobjdump"):
+        pytest.skip("cuobjdump not available")
+    so = os.path.join(ROOT, "webrtc_aecm_b200", "libaecm_b200.so")
+    res = subprocess.run(["cuobjdump", "-res-usage", so], capture_output=True, text=True).stdout
+    m = re.search(r"aecm_call_kernel\S*:\s*\n\s*REG:(\d+) STACK:(\d+) SHARED:\d+ LOCAL:(\d+)", res)
+    assert m, res[:400]
+    regs, stack, local = map(int, m.groups())
+    assert regs <= 72 and stack == 0 and local == 0, (regs, stack, local)
+    sass = subprocess.run(["cuobjdump", "-sass", so], capture_output=True, text=True).stdout
+    assert "arch = sm_100a" in sass
+    call = sass[sass.index("aecm_call_kernel"):]
+    for mnemonic in ("UBLKCP.S.G", "UBLKCP.G.S", "SYNCS.PHASECHK", "MUFU.SQRT", "CREDUX"):
+        assert mnemonic in call, mnemonic
+    assert not re.search(r"\b(LDL|STL)\b", call[:call.index("aecm_init_kernel")] if "aecm_init_kernel" in call else call)
