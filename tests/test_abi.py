@@ -93,3 +93,21 @@ def test_built_kernel_keeps_its_launch_shape_and_hardware_paths():
     for mnemonic in ("UBLKCP.S.G", "UBLKCP.G.S", "SYNCS.PHASECHK", "MUFU.SQRT", "CREDUX"):
         assert mnemonic in call, mnemonic
     assert not re.search(r"\b(LDL|STL)\b", call[:call.index("aecm_init_kernel")] if "aecm_init_kernel" in call else call)
+
+
+def test_example_program_builds_against_the_public_headers(tmp_path):
+    """examples/batch_stream.c (the INTEGRATION.md throughput loop as a complete program) compiles warning-free against
+    include/ and links against the library; without a GPU it must stop with the library's own refusal."""
+    import subprocess
+
+    exe = str(tmp_path / "batch_stream")
+    lib_dir = os.path.join(ROOT, "webrtc_aecm_b200")
+    r = subprocess.run(["gcc", "-O2", "-Wall", "-Wextra", "-Werror", "-I", os.path.join(ROOT, "include"),
+                        os.path.join(ROOT, "examples", "batch_stream.c"), "-L", lib_dir, "-laecm_b200", f"-Wl,-rpath,{lib_dir}", "-o", exe],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    import torch
+
+    if not torch.cuda.is_available():
+        run = subprocess.run([exe, "8", "2"], capture_output=True, text=True, timeout=60)
+        assert run.returncode == 1 and "no CPU path" in run.stderr
