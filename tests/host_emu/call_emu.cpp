@@ -43,14 +43,16 @@ int emu_run_stream(int fs, int cng_mode, int echo_mode, const int16_t *far, cons
         Ctx c;
         c.st = &e->st;
         c.sc = &e->sc;
-        c.far_hist = e->far_hist;
-        c.far_ring = e->far_ring;
+        c.state_base = &e->st;  // the "HBM" record is the record itself here: the write-through stores hit the same words
+        c.far_hist_base = e->far_hist;
+        c.far_ring_base = e->far_ring;
+        c.inst = 0;
         c.lane = lane;
         for (int call = 0; call < n_calls; call++) {
             const size_t o = (size_t)call * (size_t)spc;
             int r = 0;
             for (int rep = 0; rep < (far_ops ? far_ops[call] : 1); rep++) r |= api_buffer_farend(c, far + o, spc);
-            r |= api_process(c, true, near_noisy + o, near_clean ? near_clean + o : nullptr, out + o, spc, ms ? ms[call] : 40);
+            r |= api_process(c, near_noisy + o, near_clean ? near_clean + o : nullptr, out + o, spc, ms ? ms[call] : 40);
             if (lane == 0) acc |= r;
         }
     });

@@ -187,20 +187,23 @@ __device__ __forceinline__ void process_block(const Ctx &c, int in_rd, int clean
     int pos = S.far_hist_pos + 1;
     if (pos >= AECM_MAX_DELAY) pos = 0;
     {
-        uint32_t *row = reinterpret_cast<uint32_t *>(c.far_hist + pos * AECM_HIST_ROW);
+        uint32_t *row = reinterpret_cast<uint32_t *>(c.far_hist() + pos * AECM_HIST_ROW);
         const uint32_t *src = reinterpret_cast<const uint32_t *>(sc->xfa);
         row[lane] = src[lane];
         if (lane == 0) row[32] = (uint32_t)sc->xfa[64] | ((uint32_t)far_q << 16);
     }
 
     // ---- delay estimation (delay_estimator_wrapper.cc:233-262, 447-476; delay_estimator.cc:369-382) ----
-    mbar_wait(&sc->mbar_b);  // everything from here on lives in part B of the record (its copy ran behind the FFTs)
+    mbar_wait(&sc->mbar_b, sc->phase);  // everything from here on lives in part B of the record (its copy ran behind the FFTs)
     int thr_far_init = S.thr_far_init, thr_near_init = S.thr_near_init;
     const int old_head = S.bin_far_head;
     const int head = old_head == 0 ? AECM_MAX_DELAY - 1 : old_head - 1;
     const uint32_t far_bits = binary_spectrum(sc->xfa, st->thr_far, far_q, thr_far_init, lane);
     const uint32_t near_bits = binary_spectrum(sc->dfa_noisy, st->thr_near, q_noisy, thr_near_init, lane);
-    if (lane == 0) st->bin_far[head] = far_bits;
+    if (lane == 0) {
+        st->bin_far[head] = far_bits;
+        c.g()->bin_far[head] = far_bits;  // write-through: one word changes per block, so the ring is not bulk-stored back
+    }
     int minimum_probability = S.minimum_probability, last_delay_probability = S.last_delay_probability;
     int last_delay = S.last_delay;
     __syncwarp();
@@ -234,7 +237,7 @@ __device__ __forceinline__ void process_block(const Ctx &c, int in_rd, int clean
     if (delay != 0) {
         int rp = pos - delay;
         if (rp < 0) rp += AECM_MAX_DELAY;
-        const uint32_t *row = reinterpret_cast<const uint32_t *>(c.far_hist + rp * AECM_HIST_ROW);
+        const uint32_t *row = reinterpret_cast<const uint32_t *>(c.far_hist() + rp * AECM_HIST_ROW);
         uint32_t *dst = reinterpret_cast<uint32_t *>(sc->far_row);
         dst[lane] = row[lane];
         const uint32_t tail = row[32];
@@ -443,6 +446,7 @@ __device__ __forceinline__ void process_block(const Ctx &c, int in_rd, int clean
         }
     }
     if (do_store) {  // StoreAdaptiveChannel, aecm_core.cc:286-306
+        if (lane == 0) sc->stored_dirty = 1;
 #pragma unroll
         for (int p = 0; p < 3; p++) {
             const int i = lane + 32 * p;

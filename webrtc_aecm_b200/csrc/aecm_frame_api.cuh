@@ -29,24 +29,17 @@ __device__ __forceinline__ int fifo_move(int &rd, int &cnt, int cap, int k) {  /
 // ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ bool word_aligned(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 3) == 0; }
 
-// CTA-wide rendezvous that keeps the warps of a CTA inside the same block of code (instruction-cache locality);
-// every warp of the CTA executes it the same number of times per call, whatever its instance is doing.
-__device__ __forceinline__ void cta_rendezvous() {
-    if (kLockstep) __syncthreads();
-}
-
 // ------------------------------------------------------------------------------------------------
 // L2: one 80-sample frame (aecm_core.cc:501-572).  The far frame comes from the HBM jitter FIFO (far_idx >= 0:
 // index of its first sample) or from the replay buffer farend_old[slot]; near/clean come from the input planes.
-// `live` is false for warps that only keep the CTA rendezvous count (no instance, error, or start-up phase).
 // ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void process_frame(const Ctx &c, bool live, int far_idx, int slot, const int16_t *near80,
+__device__ __forceinline__ void process_frame(const Ctx &c, int far_idx, int slot, const int16_t *near80,
                                               const int16_t *clean80, int16_t *out80) {
     AecmInstanceState *st = c.st;
     AecmScalars &S = st->s;
     const int lane = c.lane;
     // FIFO cursors are read into registers (warp-uniform), updated there, and committed by lane 0
-    if (live) {
+    {
         const int in_rd = S.frm_in_rd, clean_rd = S.frm_clean_rd;
         int in_cnt = S.frm_in_cnt, clean_cnt = S.frm_clean_cnt;
         // WebRtc_WriteBuffer x2/x3, :520-524 (a full FIFO drops the excess, ring_buffer.c:150-152)
@@ -54,7 +47,7 @@ __device__ __forceinline__ void process_frame(const Ctx &c, bool live, int far_i
         const int wr = wrap_add(in_rd, in_cnt, AECM_FRM_RING);
         if (n == AECM_FRAME_LEN && ((wr | far_idx) & 1) == 0 && word_aligned(near80)) {
             const uint32_t *nw = reinterpret_cast<const uint32_t *>(near80);
-            const uint32_t *ring = reinterpret_cast<const uint32_t *>(c.far_ring);
+            const uint32_t *ring = reinterpret_cast<const uint32_t *>(c.far_ring());
             uint32_t *old = reinterpret_cast<uint32_t *>(st->farend_old[slot]);
             uint32_t *ff = reinterpret_cast<uint32_t *>(st->frm_far), *fn = reinterpret_cast<uint32_t *>(st->frm_near);
 #pragma unroll
@@ -75,7 +68,7 @@ __device__ __forceinline__ void process_frame(const Ctx &c, bool live, int far_i
             }
         } else {
             for (int k = lane; k < n; k += 32) {
-                const int16_t f = far_idx >= 0 ? c.far_ring[wrap_add(far_idx, k, AECM_FAR_RING)] : st->farend_old[slot][k];
+                const int16_t f = far_idx >= 0 ? c.far_ring()[wrap_add(far_idx, k, AECM_FAR_RING)] : st->farend_old[slot][k];
                 if (far_idx >= 0) st->farend_old[slot][k] = f;
                 const int w = wrap_add(wr, k, AECM_FRM_RING);
                 st->frm_far[w] = f;
@@ -99,8 +92,7 @@ __device__ __forceinline__ void process_frame(const Ctx &c, bool live, int far_i
     // :527-555 "while (available >= PART_LEN)": a FIFO below 64 gains 80 samples, so at most two blocks per frame
 #pragma unroll 1
     for (int blk = 0; blk < 2; blk++) {
-        cta_rendezvous();
-        if (live && S.frm_in_cnt >= AECM_PART_LEN) {
+        if (S.frm_in_cnt >= AECM_PART_LEN) {
             {
                 const int o_rd = S.frm_out_rd, o_cnt = S.frm_out_cnt;
                 process_block(c, S.frm_in_rd, S.frm_clean_rd, clean80 != nullptr, wrap_add(o_rd, o_cnt, AECM_FRM_RING),
@@ -119,7 +111,6 @@ __device__ __forceinline__ void process_frame(const Ctx &c, bool live, int far_i
             __syncwarp();
         }
     }
-    if (!live) return;
     int out_rd = S.frm_out_rd, out_cnt = S.frm_out_cnt;
     if (out_cnt < AECM_FRAME_LEN)  // :559-562: rewind, re-emitting already delivered samples
         fifo_move(out_rd, out_cnt, AECM_FRM_RING, out_cnt - AECM_FRAME_LEN);
@@ -169,10 +160,10 @@ __device__ __forceinline__ int api_buffer_farend(const Ctx &c, const int16_t *fa
     if (wr >= AECM_FAR_RING) wr -= AECM_FAR_RING;
     if (((wr | w) & 1) == 0 && word_aligned(far)) {
         const uint32_t *src = reinterpret_cast<const uint32_t *>(far);
-        uint32_t *ring = reinterpret_cast<uint32_t *>(c.far_ring);
+        uint32_t *ring = reinterpret_cast<uint32_t *>(c.far_ring());
         for (int k = c.lane; k < (w >> 1); k += 32) ring[wrap_add(wr >> 1, k, AECM_FAR_RING / 2)] = src[k];
     } else {
-        for (int k = c.lane; k < w; k += 32) c.far_ring[wrap_add(wr, k, AECM_FAR_RING)] = far[k];
+        for (int k = c.lane; k < w; k += 32) c.far_ring()[wrap_add(wr, k, AECM_FAR_RING)] = far[k];
     }
     far_cnt += w;
     __syncwarp();
@@ -210,22 +201,14 @@ __device__ __forceinline__ void est_buf_delay(DelayRegs &d, int ms, int mult) {
     if (d.time_for_delay_change > 25) d.known_delay = max(d.filt_delay - 160, 0);  // never forwarded (:390-391)
 }
 
-// `live` = the warp owns an instance and its BufferFarend/Process calls are to be executed; dead warps only keep
-// the CTA rendezvous count.
-__device__ __forceinline__ int api_process(const Ctx &c, bool live, const int16_t *near_noisy, const int16_t *near_clean,
+__device__ __forceinline__ int api_process(const Ctx &c, const int16_t *near_noisy, const int16_t *near_clean,
                                            int16_t *out, int n, int ms) {
     AecmScalars &S = c.st->s;
     const int lane = c.lane;
     const int n_frames = n / AECM_FRAME_LEN;
     int ret = 0;
-    bool processing = false;
-    if (live) {
-        if (S.init_flag != AECM_INIT_MAGIC) {
-            ret = AECM_UNINITIALIZED_ERROR;
-            live = false;
-        }
-    }
-    if (live) {
+    if (S.init_flag != AECM_INIT_MAGIC) return AECM_UNINITIALIZED_ERROR;  // :264
+    {
         if (ms < 0) { ms = 0; ret = AECM_BAD_PARAMETER_WARNING; }          // :272-278
         else if (ms > 500) { ms = 500; ret = AECM_BAD_PARAMETER_WARNING; }
         ms += 10;
@@ -273,13 +256,12 @@ __device__ __forceinline__ int api_process(const Ctx &c, bool live, const int16_
                 S.far_rd = far_rd; S.far_cnt = far_cnt;
             }
             __syncwarp();
-        } else {
-            processing = true;
+            return ret;
         }
     }
     for (int i = 0; i < n_frames; i++) {  // :358-397
         int far_idx = -2;  // "replay farend_old" (even, so that the word-wide mover still applies)
-        if (processing) {  // wrapper bookkeeping of this frame on register copies, committed before the frame is processed
+        {  // wrapper bookkeeping of this frame on register copies, committed before the frame is processed
             DelayRegs d;
             d.far_rd = S.far_rd; d.far_cnt = S.far_cnt;
             d.filt_delay = S.filt_delay; d.known_delay = S.wrapper_known_delay;
@@ -300,7 +282,7 @@ __device__ __forceinline__ int api_process(const Ctx &c, bool live, const int16_
             }
             __syncwarp();
         }
-        process_frame(c, processing, far_idx, i, near_noisy + AECM_FRAME_LEN * i,
+        process_frame(c, far_idx, i, near_noisy + AECM_FRAME_LEN * i,
                       near_clean ? near_clean + AECM_FRAME_LEN * i : nullptr, out + AECM_FRAME_LEN * i);
     }
     return ret;

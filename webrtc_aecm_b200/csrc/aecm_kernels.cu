@@ -11,7 +11,9 @@
 // 100 delay candidates -> 4 strided passes.  Warp-uniform state-machine code is computed redundantly by all lanes in
 // registers (no broadcasts); the scalars themselves are read from the shared-memory record and written back by lane 0
 // only, with __syncwarp() between the last read and the write and after it (compute-sanitizer racecheck: 0 hazards).
+#include <algorithm>
 #include <atomic>
+#include <cstddef>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -22,15 +24,15 @@ namespace {
 
 // ---- 1-D bulk async copies (TMA unit) between the HBM record and the warp's shared-memory copy ----
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(bar)));
+}
 // Issues the two bulk loads of the record (lane 0) and waits for part A; part B is waited for where it is first used.
 __device__ __forceinline__ void bulk_load_record(AecmInstanceState *dst_smem, const AecmInstanceState *src_gmem, uint32_t bytes,
-                                                 uint64_t *bar_a, uint64_t *bar_b, int lane) {
+                                                 uint64_t *bar_a, uint64_t *bar_b, uint32_t parity, int lane) {
     if (lane == 0) {
         const uint32_t a = smem_u32(bar_a), b = smem_u32(bar_b);
         const uint32_t bytes_b = bytes - AECM_STATE_PART_A;
-        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(a));
-        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(b));
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(a), "r"((uint32_t)AECM_STATE_PART_A) : "memory");
         asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
                          smem_u32(dst_smem)),
@@ -43,22 +45,43 @@ __device__ __forceinline__ void bulk_load_record(AecmInstanceState *dst_smem, co
                      : "memory");
     }
     __syncwarp();
-    mbar_wait(bar_a);
+    mbar_wait(bar_a, parity);
 }
 __device__ __forceinline__ void prefetch_line(const void *p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
-__device__ __forceinline__ void bulk_store_record(void *dst_gmem, const void *src_smem, uint32_t bytes, int lane) {
+__device__ __forceinline__ void prefetch_line_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+__device__ __forceinline__ void bulk_prefetch_l2(const void *p, uint32_t bytes) {  // bytes: multiple of 16
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_store_piece(void *rec_gmem, const void *rec_smem, uint32_t from, uint32_t to) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(reinterpret_cast<char *>(rec_gmem) + from),
+                 "r"(smem_u32(reinterpret_cast<const char *>(rec_smem) + from)), "r"(to - from)
+                 : "memory");
+}
+// Write the record back.  Two fields are left out: the binary far-end history (one word changes per block: written
+// through where it is produced, aecm_block.cuh) and the stored channel unless StoreAdaptiveChannel ran (aecm_core.cc:286-306
+// fires once per >= 30 qualifying blocks after start-up).
+__device__ __forceinline__ void bulk_store_record(AecmInstanceState *dst_gmem, const AecmInstanceState *src_smem, uint32_t bytes,
+                                                  bool stored_dirty, int lane) {
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> visible to the async proxy
     __syncwarp();
     if (lane == 0) {
-        asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst_gmem), "r"(smem_u32(src_smem)),
-                     "r"(bytes)
-                     : "memory");
+        constexpr uint32_t o_bin = offsetof(AecmInstanceState, bin_far), o_mean = offsetof(AecmInstanceState, mean_bit_counts);
+        constexpr uint32_t o_st = offsetof(AecmInstanceState, ch_stored), o_a16 = offsetof(AecmInstanceState, ch_adapt16);
+        static_assert(o_bin % 16 == 0 && o_mean % 16 == 0 && o_st % 16 == 0 && o_a16 % 16 == 0, "bulk copies move 16-byte units");
+        bulk_store_piece(dst_gmem, src_smem, 0, o_bin);
+        if (stored_dirty) {
+            bulk_store_piece(dst_gmem, src_smem, o_mean, bytes);
+        } else {
+            bulk_store_piece(dst_gmem, src_smem, o_mean, o_st);
+            bulk_store_piece(dst_gmem, src_smem, o_a16, bytes);
+        }
         asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-        asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // the shared-memory source may be released
+        asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // the shared-memory source may be reused
     }
 }
 
-// shared memory: kWarpsPerCta x (AecmInstanceState, WarpScratch)
+// shared memory: kWarpsPerCta x (AecmInstanceState, WarpScratch).  Persistent: warp w of CTA b owns the rows
+// b * kWarpsPerCta + w + k * (warps in the grid), k = 0, 1, ...; the mbarriers of its record buffer flip phase per row.
 __global__ void __launch_bounds__(kWarpsPerCta * 32, kCtasPerSm) aecm_call_kernel(AecmBatchPlanes planes, AecmCallArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -66,75 +89,118 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, kCtasPerSm) aecm_call_kerne
     AecmInstanceState *st = reinterpret_cast<AecmInstanceState *>(wbase);
     WarpScratch *sc = reinterpret_cast<WarpScratch *>(wbase + sizeof(AecmInstanceState));
 
-    const int row = blockIdx.x * kWarpsPerCta + warp;
-    const bool live = row < a.count;
-    if (!live && !kLockstep) return;
-    int inst = a.first + (live ? row : 0);
-    if (a.index && live) {  // scattered rows (combined scalar calls): the row names its instance
-        inst = __ldg(&a.index[row]);
-        if ((unsigned)inst >= (unsigned)planes.n_instances) {
-            if (a.status && lane == 0) a.status[row] = AECM_BAD_PARAMETER_ERROR;
-            if (!kLockstep) return;
-            inst = 0;
-        }
-    }
     const bool use_clean = a.near_clean != nullptr;
     const uint32_t rec_bytes = use_clean ? AECM_STATE_BYTES : AECM_STATE_BYTES_NOCLEAN;
-    AecmInstanceState *g_state = planes.state + inst;
-    const int64_t off = (int64_t)row * a.row_stride;
-    int16_t *const far_ring = planes.far_ring + (size_t)inst * AECM_FAR_RING;
-    if (live) {
-        // The audio rows of the first call are needed right after the record: start them on their way from HBM now,
-        // one 128-byte line per lane, so that their latency overlaps the record copy instead of following it.
-        const int row_bytes = a.samples_per_call * (int)sizeof(int16_t);
-        const int at = min(lane * 128, row_bytes - 1);  // lane 0.. cover the row, the last one its final byte
-        if (lane * 128 < row_bytes + 128) {
-            if (a.far) prefetch_line(reinterpret_cast<const char *>(a.far + off) + at);
-            if (a.near_noisy) prefetch_line(reinterpret_cast<const char *>(a.near_noisy + off) + at);
-            if (use_clean) prefetch_line(reinterpret_cast<const char *>(a.near_clean + off) + at);
+    if (lane == 0) {
+        mbar_init(&sc->mbar_a);
+        mbar_init(&sc->mbar_b);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        sc->phase = 0;  // parity of the mbarrier phase the next bulk load completes; kept in shared memory, not in a register
+    }
+    __syncwarp();
+
+    // The row counter lives in shared memory between rows (written and read by every lane for itself through its own
+    // word), not in a register: the block code below needs all 72 registers and nothing may be spilled to local memory.
+    volatile int *const my_row = reinterpret_cast<volatile int *>(&sc->lane_row[lane]);
+    *my_row = blockIdx.x * kWarpsPerCta + warp;
+#pragma unroll 1
+    for (;;) {
+        const int stride = (int)gridDim.x * kWarpsPerCta;
+        const int row = *my_row;
+        if (row - warp >= a.count) break;  // the CTA's rows are exhausted (same trip count for all its warps)
+        *my_row = row + stride;
+        if (kRowResync && row - warp != (int)blockIdx.x * kWarpsPerCta) __syncthreads();
+        if (row >= a.count) continue;
+        // (derived from the volatile row word on purpose: otherwise the compiler hoists the per-lane prefetch offsets and
+        // predicates out of the row loop and, with no register to keep them in, spills them to local memory)
+        const int row_bytes = (a.samples_per_call + (row < 0 ? 1 : 0)) * (int)sizeof(int16_t);
+        int inst = a.first + row;
+        if (a.index) {  // scattered rows (combined scalar calls): the row names its instance
+            inst = __ldg(&a.index[row]);
+            if ((unsigned)inst >= (unsigned)planes.n_instances) {
+                if (a.status) a.status[row] = AECM_BAD_PARAMETER_ERROR;  // (every lane, same word: rare path, no lane test to keep)
+                continue;
+            }
         }
-        bulk_load_record(st, g_state, rec_bytes, &sc->mbar_a, &sc->mbar_b, lane);
+        const AecmInstanceState *g_state = planes.state + inst;
+        const int64_t off = (int64_t)row * a.row_stride;
+        {
+            // The audio rows of the first call are needed right after the record: start them on their way from HBM now,
+            // one 128-byte line per lane, so that their latency overlaps the record copy instead of following it.
+            const int at = min(lane * 128, row_bytes - 1);  // lane 0.. cover the row, the last one its final byte
+            if (lane * 128 < row_bytes + 128) {
+                if (a.far) prefetch_line(reinterpret_cast<const char *>(a.far + off) + at);
+                if (a.near_noisy) prefetch_line(reinterpret_cast<const char *>(a.near_noisy + off) + at);
+                if (use_clean) prefetch_line(reinterpret_cast<const char *>(a.near_clean + off) + at);
+            }
+        }
+        if (lane == 0) sc->stored_dirty = 0;
+        const uint32_t phase = sc->phase;
+        bulk_load_record(st, g_state, rec_bytes, &sc->mbar_a, &sc->mbar_b, phase, lane);
         // ... and the stretch of the far-end jitter ring this call will read back (echo_control_mobile.cc:369-380:
         // up to 160 samples from the read cursor, which EstBufDelay may first move by one frame either way)
         if (lane < 6) {
             int pos = st->s.far_rd - AECM_FRAME_LEN + lane * 64;
             pos += pos < 0 ? AECM_FAR_RING : 0;
             pos -= pos >= AECM_FAR_RING ? AECM_FAR_RING : 0;
-            prefetch_line(far_ring + pos);
+            prefetch_line(planes.far_ring + (size_t)inst * AECM_FAR_RING + pos);
         }
-        if (use_clean) mbar_wait(&sc->mbar_b);  // the clean-path tail is needed from the first frame on
-    }
+        // The row this warp takes next: pull its record and its first audio rows into L2 behind this row's arithmetic, so
+        // that the bulk load at the top of the next iteration finds them there instead of in HBM.
+        {
+            const int nrow = row + stride;
+            if (nrow < a.count && !a.index) {
+                if (lane == 0) bulk_prefetch_l2(planes.state + a.first + nrow, rec_bytes);
+                const int64_t noff = (int64_t)nrow * a.row_stride;
+                if (lane >= 8 && (lane - 8) * 128 < row_bytes) {
+                    if (a.far) prefetch_line_l2(reinterpret_cast<const char *>(a.far + noff) + (lane - 8) * 128);
+                    if (a.near_noisy) prefetch_line_l2(reinterpret_cast<const char *>(a.near_noisy + noff) + (lane - 8) * 128);
+                }
+            }
+        }
+        if (use_clean) mbar_wait(&sc->mbar_b, phase);  // the clean-path tail is needed from the first frame on
 
-    Ctx c;
-    c.st = st;
-    c.sc = sc;
-    c.far_hist = planes.far_hist + (size_t)inst * AECM_MAX_DELAY * AECM_HIST_ROW;
-    c.far_ring = far_ring;
-    c.lane = lane;
+        Ctx c;
+        c.st = st;
+        c.sc = sc;
+        c.state_base = planes.state;
+        c.far_hist_base = planes.far_hist;
+        c.far_ring_base = planes.far_ring;
+        c.inst = inst;
+        c.lane = lane;
 
-    const int ms = (a.ms && live) ? (int)a.ms[row] : a.ms_uniform;
-    int status = 0;
-    for (int call = 0; call < a.n_calls; call++) {
-        const int64_t o = off + (int64_t)call * a.samples_per_call;
-        if (live && call + 1 < a.n_calls && lane * 128 < a.samples_per_call * 2) {  // the next call's audio, one line per lane
-            const int64_t nx = (o + a.samples_per_call) * (int64_t)sizeof(int16_t) + lane * 128;
-            if (a.far) prefetch_line(reinterpret_cast<const char *>(a.far) + nx);
-            if (a.near_noisy) prefetch_line(reinterpret_cast<const char *>(a.near_noisy) + nx);
+        // (through the lane's own shared-memory word: the clamped value would otherwise be hoisted out of the call loop and,
+        // with no register left for it, spilled to local memory)
+        volatile int *const my_ms = reinterpret_cast<volatile int *>(&sc->lane_ms[lane]);
+        *my_ms = a.ms ? (int)a.ms[row] : a.ms_uniform;
+        int status = 0;
+#pragma unroll 1
+        for (int call = 0; call < a.n_calls; call++) {
+            // (recomputed from the row and call numbers instead of carried: keeps two registers free across the block code)
+            const int64_t o = (int64_t)row * a.row_stride + (int64_t)call * a.samples_per_call;
+            if (call + 1 < a.n_calls && lane * 128 < row_bytes) {  // the next call's audio, one line per lane
+                const int64_t nx = (o + a.samples_per_call) * (int64_t)sizeof(int16_t) + lane * 128;
+                if (a.far) prefetch_line(reinterpret_cast<const char *>(a.far) + nx);
+                if (a.near_noisy) prefetch_line(reinterpret_cast<const char *>(a.near_noisy) + nx);
+            }
+            if (a.far && (!a.far_mask || a.far_mask[(size_t)call * a.mask_stride + row])) {
+                const int r = api_buffer_farend(c, a.far + o, a.samples_per_call);
+                if (status == 0) status = r;
+            }
+            if (a.near_noisy) {
+                const int r = api_process(c, a.near_noisy + o, use_clean ? a.near_clean + o : nullptr, a.out + o,
+                                          a.samples_per_call, *my_ms);
+                if (status == 0) status = r;
+            }
         }
-        if (live && a.far && (!a.far_mask || a.far_mask[(size_t)call * a.mask_stride + row])) {
-            const int r = api_buffer_farend(c, a.far + o, a.samples_per_call);
-            if (status == 0) status = r;
-        }
-        if (a.near_noisy) {
-            const int r = api_process(c, live, a.near_noisy + o, use_clean ? a.near_clean + o : nullptr, a.out + o,
-                                      a.samples_per_call, ms);
-            if (status == 0) status = r;
+        mbar_wait(&sc->mbar_b, sc->phase);  // (a start-up call never touched part B: make sure it has landed before it is stored back)
+        const bool stored_dirty = sc->stored_dirty != 0;  // written by lane 0 before the __syncwarp that ended its block
+        bulk_store_record(c.g(), st, rec_bytes, stored_dirty, lane);
+        if (lane == 0) {
+            if (a.status) a.status[row] = status;
+            sc->phase ^= 1;  // ordered before the next row's reads by the __syncwarp of its bulk_load_record
         }
     }
-    if (!live) return;
-    mbar_wait(&sc->mbar_b);  // (a start-up call never touched part B: make sure it has landed before it is stored back)
-    bulk_store_record(g_state, st, rec_bytes, lane);
-    if (a.status && lane == 0) a.status[row] = status;
 }
 
 __global__ void aecm_init_kernel(AecmBatchPlanes planes, int first, int count, int fs) {
@@ -246,7 +312,14 @@ int aecm_cuda_launch_call(const AecmBatchPlanes *p, const AecmCallArgs *a, void 
         if (e != cudaSuccess) return (int)e;
         attr_set[dev] = true;
     }
-    const int blocks = (a->count + kWarpsPerCta - 1) / kWarpsPerCta;
+    static std::atomic<int> sm_count[64];  // persistent grid: at most (resident CTAs per SM) x (SMs) CTAs
+    if (!sm_count[dev]) {
+        int n = 0;
+        cudaError_t e = cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+        if (e != cudaSuccess || n <= 0) return (int)(e != cudaSuccess ? e : cudaErrorInvalidDevice);
+        sm_count[dev] = n;
+    }
+    const int blocks = std::min((a->count + kWarpsPerCta - 1) / kWarpsPerCta, sm_count[dev] * kCtasPerSm);
     aecm_call_kernel<<<blocks, kWarpsPerCta * 32, smem, static_cast<cudaStream_t>(stream)>>>(*p, *a);
     g_launches++;
     return (int)cudaGetLastError();

@@ -16,16 +16,20 @@ namespace {
 
 constexpr unsigned kFull = 0xffffffffu;
 // One 28-warp CTA per SM: the warps of an SM start together and drift less through the ~50 KB of straight-line
-// code than seven independent 4-warp CTAs do (measured: +26 % throughput), at identical residency.
+// code than seven independent 4-warp CTAs do (measured: +26 % throughput), at identical residency.  The kernel is
+// persistent: at most one CTA per SM is launched and every warp walks the rows r, r + (warps in the grid), ...
+// 28 warps/SM: BASELINE configs[1] (4096 instances) is a single pass on 148 SMs.
 #ifndef AECM_WARPS_PER_CTA
 #define AECM_WARPS_PER_CTA 28
 #endif
 constexpr int kWarpsPerCta = AECM_WARPS_PER_CTA;
 constexpr int kCtasPerSm = kWarpsPerCta >= 28 ? 1 : 28 / kWarpsPerCta;
-#ifndef AECM_LOCKSTEP
-#define AECM_LOCKSTEP 0
+// CTA-wide rendezvous between two rows of the persistent loop (re-aligns the warps of an SM on the instruction stream
+// once per row; 0 = warps run free).  Measured both ways, see DESIGN.md 4.1.
+#ifndef AECM_ROW_RESYNC
+#define AECM_ROW_RESYNC 0
 #endif
-constexpr bool kLockstep = AECM_LOCKSTEP != 0;  // CTA-wide rendezvous before every block (I-cache locality experiment)  // 28 warps/SM: BASELINE configs[1] (4096 instances) is a single wave on 148 SMs
+constexpr bool kRowResync = AECM_ROW_RESYNC != 0;
 
 // ---- algorithm constants, aecm_defines.h:28-85 ----
 constexpr int kConvLen = 512;
@@ -115,30 +119,48 @@ struct __align__(16) WarpScratch {
     uint16_t xfa[72], dfa_noisy[72], dfa_clean[72], far_row[72];
     uint64_t mbar_a;       // mbarriers of the record's two bulk loads (part A: scalars/FIFOs, part B: the rest)
     uint64_t mbar_b;
+    uint32_t stored_dirty; // ch_stored was rewritten during this launch (StoreAdaptiveChannel): it has to be written back
+    uint32_t phase;        // parity of the mbarrier phase of this row's bulk loads (flips from row to row)
+    uint32_t pad_[2];
+    int32_t lane_row[32];  // the persistent loop's row counter, one word per lane (see aecm_call_kernel)
+    int32_t lane_ms[32];   // msInSndCardBuf of the current row, one word per lane
 };
 
 struct Ctx {
     AecmInstanceState *st;  // shared-memory copy of the record
     WarpScratch *sc;
-    uint16_t *far_hist;     // this instance's 100 x 66 rows in HBM
-    int16_t *far_ring;      // this instance's 4000-sample jitter FIFO in HBM
+    // The three HBM planes are addressed as (plane base, instance): the bases are kernel parameters (uniform, never
+    // held in per-thread registers), so an instance costs one register here instead of three 64-bit pointers.
+    AecmInstanceState *state_base;
+    uint16_t *far_hist_base;
+    int16_t *far_ring_base;
+    int inst;
     int lane;
+    // the record in HBM (write-through target of the fields that are not bulk-stored back)
+    __device__ __forceinline__ AecmInstanceState *g() const { return state_base + inst; }
+    // this instance's 100 x 66 rows in HBM
+    __device__ __forceinline__ uint16_t *far_hist() const { return far_hist_base + (size_t)inst * (AECM_MAX_DELAY * AECM_HIST_ROW); }
+    // this instance's 4000-sample jitter FIFO in HBM
+    __device__ __forceinline__ int16_t *far_ring() const { return far_ring_base + (size_t)inst * AECM_FAR_RING; }
 };
 
-// wait for a bulk load (phase 0 of its mbarrier); returns at once when the data already arrived
-__device__ __forceinline__ void mbar_wait(uint64_t *bar) {
+// wait for a bulk load (the phase of its mbarrier with the given parity: the persistent loop alternates 0, 1, 0, ...
+// from row to row); returns at once when the data already arrived
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
 #ifdef AECM_HOST_EMU  // tests/host_emu: the record is already in place
     (void)bar;
+    (void)parity;
 #else
     asm volatile(
         "{\n"
         ".reg .pred p;\n"
         "WAIT_RECORD:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], 0;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
         "@p bra DONE_RECORD;\n"
         "bra WAIT_RECORD;\n"
         "DONE_RECORD:\n"
-        "}\n" ::"r"((uint32_t)__cvta_generic_to_shared(bar))
+        "}\n" ::"r"((uint32_t)__cvta_generic_to_shared(bar)),
+        "r"(parity)
         : "memory");
 #endif
 }
