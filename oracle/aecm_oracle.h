@@ -171,6 +171,9 @@ OraclePool *oracle_pool_create(int impl, const char *ref_lib_path, int n, int fs
 /* runs n_calls x (BufferFarend + Process) on every instance; returns the OR of all return codes */
 int oracle_pool_run(OraclePool *p, const int16_t *far, const int16_t *near_noisy, const int16_t *near_clean,
                     int16_t *out, int64_t row_stride, int spc, int n_calls, int ms, double *seconds);
+/* throughput variant: tile_rows distinct streams in the planes, instance i is fed row i % tile_rows, output dropped */
+int oracle_pool_run_tiled(OraclePool *p, const int16_t *far, const int16_t *near_noisy, int tile_rows, int64_t row_stride,
+                          int spc, int n_calls, int ms, double *seconds);
 void oracle_pool_free(OraclePool *p);
 
 #ifdef __cplusplus

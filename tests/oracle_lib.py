@@ -65,6 +65,9 @@ def oracle():
         lib.oracle_pool_run.restype = C.c_int
         lib.oracle_pool_run.argtypes = [C.c_void_p] + [C.c_void_p] * 4 + [C.c_int64, C.c_int, C.c_int, C.c_int,
                                                                            C.POINTER(C.c_double)]
+        lib.oracle_pool_run_tiled.restype = C.c_int
+        lib.oracle_pool_run_tiled.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int64, C.c_int, C.c_int, C.c_int,
+                                              C.POINTER(C.c_double)]
         lib.oracle_pool_free.restype = None
         lib.oracle_pool_free.argtypes = [C.c_void_p]
         _lib = lib
@@ -269,6 +272,15 @@ class CpuPool:
         acc = self.lib.oracle_pool_run(self.h, _ptr(far), _ptr(near), _ptr(clean), _ptr(out), far.shape[1],
                                        samples_per_call, far.shape[1] // samples_per_call, ms, C.byref(secs))
         return out, acc, secs.value
+
+    def run_tiled(self, far, near, samples_per_call=160, ms=40):
+        """Throughput runs: far/near hold R <= n distinct streams [R, T]; instance i is fed row i % R and its output is
+        dropped.  Returns (or_of_return_codes, seconds)."""
+        assert far.flags["C_CONTIGUOUS"] and near.flags["C_CONTIGUOUS"] and far.shape == near.shape
+        secs = C.c_double(0)
+        acc = self.lib.oracle_pool_run_tiled(self.h, _ptr(far), _ptr(near), far.shape[0], far.shape[1], samples_per_call,
+                                             far.shape[1] // samples_per_call, ms, C.byref(secs))
+        return acc, secs.value
 
     def close(self):
         if self.h:

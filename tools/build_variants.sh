@@ -1,0 +1,24 @@
+#!/bin/bash
+# Builds A/B variants of the library into variants/ (git-ignored, travels to the GPU box; selected with AECM_B200_LIB):
+#   v7.so          the round-1 kernel (one CTA per 28 rows, no row loop), from git
+#   v8_free.so     the persistent kernel without the CTA-wide rendezvous between rows (-DAECM_ROW_RESYNC=0)
+#   v8_cta14.so    two 14-warp CTAs per SM instead of one 28-warp CTA (-DAECM_WARPS_PER_CTA=14)
+#   v8_nobin64.so  MEASUREMENT ONLY, wrong output: the one-live-lane pass for bin 64 compiled out (-DAECM_BIN_PASSES=2)
+set -e
+ROOT=$(cd "$(dirname "$0")/.." && pwd)
+mkdir -p "$ROOT/variants"
+build() {  # name, source tree, extra nvcc flags
+  make -s -C "$2/webrtc_aecm_b200/csrc" clean >/dev/null 2>&1 || true
+  make -s -C "$2/webrtc_aecm_b200/csrc" NVEXTRA="$3" "$2/webrtc_aecm_b200/libaecm_b200.so"
+  cp "$2/webrtc_aecm_b200/libaecm_b200.so" "$ROOT/variants/$1.so"
+}
+TMP=$(mktemp -d)
+git -C "$ROOT" archive 7f30022 webrtc_aecm_b200/csrc include | tar -x -C "$TMP"
+build v7 "$TMP" ""
+rm -rf "$TMP"; TMP=$(mktemp -d)
+(cd "$ROOT" && tar -c webrtc_aecm_b200/csrc/*.c webrtc_aecm_b200/csrc/*.cu webrtc_aecm_b200/csrc/*.cuh webrtc_aecm_b200/csrc/*.h webrtc_aecm_b200/csrc/Makefile include tools/scalar_api_bench.c) | tar -x -C "$TMP"
+build v8_free "$TMP" "-DAECM_ROW_RESYNC=0"
+build v8_cta14 "$TMP" "-DAECM_WARPS_PER_CTA=14"
+build v8_nobin64 "$TMP" "-DAECM_BIN_PASSES=2"
+rm -rf "$TMP"
+ls -la "$ROOT/variants"

@@ -49,7 +49,7 @@ __device__ __forceinline__ void time_to_frequency(const Ctx &c, const int16_t *c
     for (int n = 0; n < NS; n++) {
         uint32_t sum = 0;
 #pragma unroll
-        for (int p = 0; p < 3; p++) {
+        for (int p = 0; p < kBinPasses; p++) {
             const int i = p < 2 ? lane + 32 * p : 64;
             const int re = bre[n][p];
             const int im = (i == 0 || i == 64) ? 0 : s16(-bim[n][p]);  // :188-190, :296-297
@@ -253,7 +253,7 @@ __device__ __forceinline__ void process_block(const Ctx &c, int in_rd, int clean
     {
         uint32_t e_far = 0, e_adapt = 0, e_stored = 0;
 #pragma unroll
-        for (int p = 0; p < 3; p++) {
+        for (int p = 0; p < kBinPasses; p++) {
             const int i = lane + 32 * p;
             if (i < AECM_BINS) {
                 const int f = far_spec[i];
@@ -299,7 +299,7 @@ __device__ __forceinline__ void process_block(const Ctx &c, int in_rd, int clean
         first_vad = 0;
         if (echo_adapt_log0 > near_log0) {
 #pragma unroll
-            for (int p = 0; p < 3; p++) {
+            for (int p = 0; p < kBinPasses; p++) {
                 const int i = lane + 32 * p;
                 if (i < AECM_BINS) st->ch_adapt16[i] = (int16_t)(st->ch_adapt16[i] >> 3);
             }
@@ -345,7 +345,7 @@ __device__ __forceinline__ void process_block(const Ctx &c, int in_rd, int clean
     const int q_n = q_noisy;
     if (mu) {
 #pragma unroll
-        for (int p = 0; p < 3; p++) {
+        for (int p = 0; p < kBinPasses; p++) {
             const int i = lane + 32 * p;
             if (i < AECM_BINS) {
                 const int ch32 = st->ch_adapt32[i];
@@ -422,7 +422,7 @@ __device__ __forceinline__ void process_block(const Ctx &c, int in_rd, int clean
                 ((mse_stored_old << kMseResolution) < (kMinMseDiff * mse_adapt_old))) {
                 // ResetAdaptiveChannel, aecm_core.cc:308-323
 #pragma unroll
-                for (int p = 0; p < 3; p++) {
+                for (int p = 0; p < kBinPasses; p++) {
                     const int i = lane + 32 * p;
                     if (i < AECM_BINS) {
                         const int v = st->ch_stored[i];
@@ -448,7 +448,7 @@ __device__ __forceinline__ void process_block(const Ctx &c, int in_rd, int clean
     if (do_store) {  // StoreAdaptiveChannel, aecm_core.cc:286-306
         if (lane == 0) sc->stored_dirty = 1;
 #pragma unroll
-        for (int p = 0; p < 3; p++) {
+        for (int p = 0; p < kBinPasses; p++) {
             const int i = lane + 32 * p;
             if (i < AECM_BINS) {
                 const int v = st->ch_adapt16[i];
@@ -500,7 +500,7 @@ __device__ __forceinline__ void process_block(const Ctx &c, int in_rd, int clean
     const int dq_clean = s16(q_clean - q_clean_old);
     const int z16_sup = norm_w16(sup_gain) + 1;
 #pragma unroll
-    for (int p = 0; p < 3; p++) {
+    for (int p = 0; p < kBinPasses; p++) {
         const int i = lane + 32 * p;
         hnl[p] = 0;
         if (i < AECM_BINS) {
@@ -560,11 +560,11 @@ __device__ __forceinline__ void process_block(const Ctx &c, int in_rd, int clean
     if (S.mult == 2) {  // wideband only, :618-648 (mult is only written by Init)
         int part = 0;
 #pragma unroll
-        for (int p = 0; p < 3; p++) hnl[p] = (hnl[p] * hnl[p]) >> 14;
+        for (int p = 0; p < kBinPasses; p++) hnl[p] = (hnl[p] * hnl[p]) >> 14;
         if (lane >= 4 && lane <= 24) part = hnl[0];
         const int avg = __reduce_add_sync(kFull, part) / 21;
 #pragma unroll
-        for (int p = 0; p < 3; p++) {
+        for (int p = 0; p < kBinPasses; p++) {
             const int i = lane + 32 * p;
             if (i >= 24 && hnl[p] > avg) hnl[p] = avg;
         }
@@ -573,7 +573,7 @@ __device__ __forceinline__ void process_block(const Ctx &c, int in_rd, int clean
     int ere[3], eim[3];
     const int nlp_gain = num_pos < 3 ? 0 : kOneQ14;
 #pragma unroll
-    for (int p = 0; p < 3; p++) {
+    for (int p = 0; p < kBinPasses; p++) {
         const int i = lane + 32 * p;
         ere[p] = eim[p] = 0;
         if (i < AECM_BINS) {
@@ -597,7 +597,7 @@ __device__ __forceinline__ void process_block(const Ctx &c, int in_rd, int clean
         int track;
         if (noise_est_ctr < 100) { noise_est_ctr++; track = 6; } else { track = 9; }
 #pragma unroll
-        for (int p = 0; p < 3; p++) {
+        for (int p = 0; p < kBinPasses; p++) {
             const int i = lane + 32 * p;
             if (i < AECM_BINS) {
                 int ne = st->noise_est[i];
@@ -651,7 +651,7 @@ __device__ __forceinline__ void process_block(const Ctx &c, int in_rd, int clean
         const int4 lb = __ldg(&kLaneTables.bins[lane]);  // tile words of bins lane, lane+32 and of their mirrors
         const int words[2] = {lb.x, lb.y}, mirrors[2] = {lb.z, lb.w};
 #pragma unroll
-        for (int p = 0; p < 3; p++) {
+        for (int p = 0; p < kBinPasses; p++) {
             const int i = p < 2 ? lane + 32 * p : 64;
             if (p < 2 || lane == 0) {
                 const int nim = s16(-eim[p]);  // aecm_core_c.cc:206-214

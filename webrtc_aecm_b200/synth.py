@@ -36,14 +36,18 @@ def _noise16(seed: int, inst: np.ndarray, t: np.ndarray, salt: int) -> np.ndarra
 
 
 def synth_streams(n_instances: int, n_samples: int, fs: int = 16000, seed: int = 0xAEC0,
-                  delay_ms=40, kind: str = "echo", first_instance: int = 0, first_sample: int = 0):
+                  delay_ms=40, kind: str = "echo", first_instance: int = 0, first_sample: int = 0, instances=None):
     """Return (far, near) int16 arrays of shape [n_instances, n_samples].
 
     ``delay_ms`` is a scalar or a per-instance array: the acoustic echo delay in ms.
-    ``first_instance``/``first_sample`` let shards/chunks generate their slice of one global stream.
+    ``first_instance``/``first_sample`` let shards/chunks generate their slice of one global stream;
+    ``instances`` (array of global instance numbers, length n_instances) picks arbitrary rows of it instead.
     """
     with np.errstate(over="ignore"):
-        inst = (np.arange(n_instances, dtype=np.int64) + first_instance)[:, None]
+        if instances is not None:
+            inst = np.asarray(instances, dtype=np.int64).reshape(n_instances)[:, None]
+        else:
+            inst = (np.arange(n_instances, dtype=np.int64) + first_instance)[:, None]
         delay = np.broadcast_to(np.asarray(delay_ms, dtype=np.int64), (n_instances,))[:, None] * (fs // 1000)
         max_d = int(delay.max()) + 4
         # generate the far end with a pre-roll so the delayed copy exists from sample 0
@@ -104,14 +108,17 @@ def _t_hash32(x):
 
 
 def synth_streams_torch(n_instances: int, n_samples: int, fs: int = 16000, seed: int = 0xAEC0, delay_ms=40,
-                        kind: str = "echo", first_instance: int = 0, first_sample: int = 0, device="cuda"):
+                        kind: str = "echo", first_instance: int = 0, first_sample: int = 0, device="cuda", instances=None):
     """torch twin of :func:`synth_streams`; returns (far, near) int16 tensors on ``device``."""
     import torch
 
     M = 0xFFFFFFFF
     dev = torch.device(device)
     i64 = torch.int64
-    inst = (torch.arange(n_instances, dtype=i64, device=dev) + first_instance)[:, None]
+    if instances is not None:
+        inst = torch.as_tensor(instances, dtype=i64, device=dev).reshape(n_instances)[:, None]
+    else:
+        inst = (torch.arange(n_instances, dtype=i64, device=dev) + first_instance)[:, None]
     delay = torch.as_tensor(delay_ms, dtype=i64, device=dev).expand(n_instances).clone()[:, None] * (fs // 1000)
     max_d = int(delay.max().item()) + 4
     t = (torch.arange(-max_d, n_samples, dtype=i64, device=dev) + first_sample)[None, :]
