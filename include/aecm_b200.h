@@ -75,7 +75,11 @@ typedef struct {
     const uint8_t *farendMask;    /* optional [nCalls][count] */
     int32_t *status;              /* optional [count] */
     const int32_t *instanceIndex; /* optional [count]: plane row r is instance instanceIndex[r] instead of first + r;
-                                     the indices must be distinct (one warp per row, no locking); `first` is ignored */
+                                     the indices must be distinct (one warp per row, no locking); `first` is ignored.
+                                     The host-plane calls reject an out-of-range or repeated index with
+                                     AECM_BAD_PARAMETER_ERROR before anything is enqueued; for the device array of
+                                     AecmB200_ProcessStreamDevice distinctness is the caller's responsibility (an
+                                     out-of-range row only gets AECM_BAD_PARAMETER_ERROR in its status) */
 } AecmB200StreamArgs;
 
 /* Host-memory planes: copies in, runs, copies out and waits (pinned planes avoid the staging copy). */
@@ -86,7 +90,9 @@ int32_t AecmB200_ProcessStream(AecmB200Batch *batch, const AecmB200StreamArgs *h
  * the copies of one slot overlap the kernels and copies of the others.  A call occupies its slot for H2D + kernel +
  * D2H, so keeping the PCIe link busy takes three or four calls in flight (round-robin over the slots, waiting for
  * the oldest).  The host planes (pinned for real overlap) and the status array must stay valid until Wait.  Tip: if
- * the dense near plane starts exactly where the dense far plane ends, both cross PCIe in one transfer. */
+ * the dense near plane starts exactly where the dense far plane ends, both cross PCIe in one transfer.
+ * A Submit that fails (bad arguments, CUDA error) leaves its slot free: whatever it had enqueued is drained first and
+ * nothing is delivered for it; Wait on a free slot returns 0 and touches no status array. */
 int32_t AecmB200_SubmitStream(AecmB200Batch *batch, const AecmB200StreamArgs *hostArgs, int32_t slot);
 int32_t AecmB200_WaitStream(AecmB200Batch *batch, int32_t slot);
 int32_t AecmB200_NumStreamSlots(void);
@@ -134,6 +140,16 @@ void AecmB200_ScalarApiStats(void *aecmInst, int64_t *rounds, int64_t *requests)
  * arguments [first, first + count) on the current device and returns how many differ from the reference's
  * bit-by-bit construction (0 expected; negative = CUDA error). */
 int64_t AecmB200_SelfTestSqrtFloor(uint32_t first, uint32_t count);
+/* Diagnostics: runs the kernel's own warp FFT (the code and tables of the hot path) on n host vectors on the current
+ * device, for known-answer tests against the reference's WebRtcSpl_RealForwardFFT / WebRtcSpl_RealInverseFFT
+ * (real_fft.c:47-102 over complex_fft.c:241-491, order 7).
+ *   Forward: in [n][128] real samples (already windowed) -> out [n][130] = bins 0..64 as interleaved re, im, exactly
+ *            what WebRtcSpl_RealForwardFFT returns; twoSignals != 0 runs the far+near interleaved variant on vector pairs.
+ *   Inverse: in [n][130] = bins 0..64 interleaved, as handed to WebRtcSpl_RealInverseFFT -> out [n][128] real samples
+ *            and scale[n] = the value WebRtcSpl_RealInverseFFT returns (block-floating shifts, complex_fft.c:381-396).
+ * Return: 0, AECM_NULL_POINTER_ERROR, AECM_BAD_PARAMETER_ERROR, or AECM_UNSPECIFIED_ERROR when CUDA failed. */
+int32_t AecmB200_SelfTestFftForward(const int16_t *in, int16_t *out, int32_t n, int32_t twoSignals);
+int32_t AecmB200_SelfTestFftInverse(const int16_t *in, int16_t *out, int32_t *scale, int32_t n);
 int32_t AecmB200_DeviceCount(void);
 
 #ifdef __cplusplus

@@ -176,3 +176,31 @@ def far_mask(case, n_calls):
     if k > 0:
         m[(np.arange(n_calls) % k) == k - 1, :] = 0
     return m
+
+
+def fft_adversarial_vectors(rng=None):
+    """Inputs for the device FFT known-answer test beyond the committed golden set: random, impulses, full scale,
+    alternating extremes, and inverse inputs whose per-stage peaks straddle the block-floating thresholds 13573 / 27146
+    (complex_fft.c:386-396)."""
+    rng = rng or np.random.default_rng(128)
+    fwd = [rng.integers(-32768, 32768, 128), rng.integers(-2000, 2000, 128), np.zeros(128), np.full(128, 32767),
+           np.full(128, -32768), np.where(np.arange(128) % 2, 32767, -32768), np.eye(1, 128, 0)[0] * 32767,
+           np.eye(1, 128, 127)[0] * -32768]
+    fwd += [rng.integers(-a, a + 1, 128) for a in (1, 3, 100, 8191, 16384, 23170, 32767) for _ in range(6)]
+    inv = []
+    for amp in (0, 1, 50, 848, 849, 1696, 1697, 3393, 3394, 6786, 6787, 13572, 13573, 13574, 27145, 27146, 27147, 32767):
+        for shape in range(4):
+            v = np.zeros(130, dtype=np.int64)
+            if shape == 0:
+                v[:] = rng.integers(-amp, amp + 1, 130)
+            elif shape == 1:
+                v[2 * int(rng.integers(0, 65))] = amp
+            elif shape == 2:
+                v[::2] = amp
+            else:
+                v[:] = np.where(rng.integers(0, 2, 130) > 0, amp, -amp)
+            v[1] = 0  # bins 0 and 64 are real (aecm_core_c.cc:206-214 hands them over that way)
+            v[129] = 0
+            inv.append(v)
+    inv += [np.where(np.arange(130) % 2, 0, -32768)]
+    return np.array(fwd, dtype=np.int16), np.array(inv, dtype=np.int16)

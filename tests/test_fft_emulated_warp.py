@@ -52,3 +52,24 @@ def test_inverse_fft_and_scale_match_reference_vectors(emu):
         scale[i] = emu.emu_fft128_inverse(iin[i].ctypes.data_as(C.c_void_p), got[i].ctypes.data_as(C.c_void_p))
     np.testing.assert_array_equal(scale, iscale)
     np.testing.assert_array_equal(got, iout)
+
+
+def test_adversarial_family_matches_reference_answers(emu):
+    """tests/golden/fft_adversarial.npz (reference answers for tests/cases.py:fft_adversarial_vectors -- impulses, full scale,
+    per-stage peaks straddling 13573 / 27146, scales 0..8): the device FFT on the emulated warp, both forward variants."""
+    A = np.load(os.path.join(HERE, "golden", "fft_adversarial.npz"))
+    fwd, inv = np.ascontiguousarray(A["fwd_in"]), np.ascontiguousarray(A["inv_in"])
+    got = np.zeros_like(A["fwd_out"])
+    for i in range(len(fwd)):
+        emu.emu_fft128_forward(fwd[i].ctypes.data_as(C.c_void_p), got[i].ctypes.data_as(C.c_void_p), 1)
+    np.testing.assert_array_equal(got, A["fwd_out"])
+    for i in range(0, len(fwd) - 1, 2):
+        pair = np.ascontiguousarray(fwd[i:i + 2])
+        g2 = np.zeros((2, 130), dtype=np.int16)
+        emu.emu_fft128_forward(pair.ctypes.data_as(C.c_void_p), g2.ctypes.data_as(C.c_void_p), 2)
+        np.testing.assert_array_equal(g2, A["fwd_out"][i:i + 2])
+    got, sc = np.zeros_like(A["inv_out"]), np.zeros(len(inv), dtype=np.int32)
+    for i in range(len(inv)):
+        sc[i] = emu.emu_fft128_inverse(inv[i].ctypes.data_as(C.c_void_p), got[i].ctypes.data_as(C.c_void_p))
+    np.testing.assert_array_equal(sc, A["inv_scale"])
+    np.testing.assert_array_equal(got, A["inv_out"])

@@ -129,22 +129,53 @@ def test_state_matches_oracle_field_by_field():
 
 
 def test_full_batch_4096_properties():
-    """BASELINE configs[1] size.  (a) a sampled subset equals the oracle bit for bit; (b) instances fed
-    identical streams produce identical outputs wherever they sit in the batch; (c) every instance differs from
+    """BASELINE configs[1] size, run far enough (460 calls = 1150 blocks, fused 46 per launch) that every instance of the
+    FULL batch is in steady state (startupState == 2, channel store/reset decisions running).  64 distinct streams are
+    scattered over the 4096 instances: every instance must equal the oracle -- and the unmodified reference library when
+    it travelled along -- on its stream, bit for bit, wherever it sits in the batch; and every instance differs from
     pass-through once the canceller is active."""
     from webrtc_aecm_b200 import AecmBatch
 
-    fs, spc, n, calls, uniq = 16000, 160, 4096, 60, 64
+    fs, spc, n, calls, uniq, fuse = 16000, 160, 4096, 460, 64, 46
     far_u, near_u = synth_streams(uniq, calls * spc, fs, seed=4096, delay_ms=np.arange(uniq) % 100)
     perm = (np.arange(n) * 37) % uniq  # scatter the 64 distinct streams over the batch
-    far, near = np.ascontiguousarray(far_u[perm]), np.ascontiguousarray(near_u[perm])
     b = AecmBatch(n, 0)
     assert b.init(fs) == 0
-    rc, out, status = b.process_stream(far, near, samples_per_call=spc)
-    assert rc == 0 and not status.any()
+    out = np.zeros((n, calls * spc), dtype=np.int16)
+    for c0 in range(0, calls, fuse):
+        sl = slice(c0 * spc, (c0 + fuse) * spc)
+        rc, o, status = b.process_stream(np.ascontiguousarray(far_u[perm, sl]), np.ascontiguousarray(near_u[perm, sl]),
+                                         samples_per_call=spc)
+        assert rc == 0 and not status.any()
+        out[:, sl] = o
+    for k in (0, n // 2, n - 1):
+        st = b.read_state(k).s
+        assert st.startup_state == 2 and st.tot_count == 1150
     want, _, _ = ol.run_streams(far_u, near_u, fs=fs, impl="oracle")
     np.testing.assert_array_equal(out, want[perm])
-    assert (out[:, 8 * spc:] != near[:, 8 * spc:]).any(axis=1).all()
+    if ol.ref_path():
+        ref, _, _ = ol.run_streams(far_u, near_u, fs=fs, impl="ref")
+        np.testing.assert_array_equal(out[:uniq * 37:37], ref[perm[:uniq * 37:37]])  # 64 sampled instances, all 64 streams
+        np.testing.assert_array_equal(want, ref)
+    assert (out[:, 8 * spc:] != near_u[perm][:, 8 * spc:]).any(axis=1).all()
+    b.close()
+
+
+def test_c4_262144_instances_on_one_gpu():
+    """BASELINE configs[3] at its stated size on one GPU (the persistent kernel walks 64 rows per warp): 262144 instances,
+    128 distinct streams dealt over them; EVERY instance must reproduce the oracle's output for its stream."""
+    from webrtc_aecm_b200 import AecmBatch
+
+    fs, spc, n, calls, uniq = 16000, 160, 262144, 24, 128
+    far_u, near_u = synth_streams(uniq, calls * spc, fs, seed=262144, delay_ms=np.arange(uniq) % 110)
+    idx = (np.arange(n) * 61) % uniq
+    b = AecmBatch(n, 0)
+    assert b.init(fs) == 0
+    rc, out, status = b.process_stream(np.ascontiguousarray(far_u[idx]), np.ascontiguousarray(near_u[idx]), samples_per_call=spc)
+    assert rc == 0 and not status.any()
+    want, _, _ = ol.run_streams(far_u, near_u, fs=fs, impl="oracle")
+    bad = np.nonzero((out != want[idx]).any(axis=1))[0]
+    assert bad.size == 0, f"{bad.size} instances differ, first {bad[:8]}"
     b.close()
 
 
@@ -249,6 +280,41 @@ def test_device_floor_sqrt_is_exact_on_all_2_to_31_arguments():
     L = api.lib()
     assert L.AecmB200_SelfTestSqrtFloor(0, 1 << 30) == 0
     assert L.AecmB200_SelfTestSqrtFloor(1 << 30, 1 << 30) == 0
+
+
+def test_device_fft_known_answers():
+    """The kernel's own warp FFT (AecmB200_SelfTestFft*: the register-resident forward128 / inverse128 with the production
+    tables, PRMT packing and redux peaks) on the GPU against (a) the committed golden vectors produced by the reference's
+    WebRtcSpl_RealForwardFFT / WebRtcSpl_RealInverseFFT, returned scale included, and (b) a larger adversarial set
+    (impulses, full scale, per-stage peaks straddling 13573 / 27146) with answers from the same reference functions
+    (tests/golden/fft_adversarial.npz, written by tools/make_golden.py)."""
+    import ctypes as C
+
+    from webrtc_aecm_b200 import api
+
+    L = api.lib()
+    vp = lambda a: a.ctypes.data_as(C.c_void_p)
+    fin, fout = np.ascontiguousarray(VEC["fft_fwd_in"]), VEC["fft_fwd_out"]
+    iin, iout, iscale = np.ascontiguousarray(VEC["fft_inv_in"]), VEC["fft_inv_out"], VEC["fft_inv_scale"]
+    for two in (0, 1):
+        got = np.zeros_like(fout)
+        assert L.AecmB200_SelfTestFftForward(vp(fin), vp(got), len(fin), two) == 0
+        np.testing.assert_array_equal(got, fout)
+    got, sc = np.zeros_like(iout), np.zeros(len(iin), dtype=np.int32)
+    assert L.AecmB200_SelfTestFftInverse(vp(iin), vp(got), vp(sc), len(iin)) == 0
+    np.testing.assert_array_equal(sc, iscale)
+    np.testing.assert_array_equal(got, iout)
+
+    A = np.load(os.path.join(GOLD, "fft_adversarial.npz"))  # reference answers for tests/cases.py:fft_adversarial_vectors
+    fwd, inv = np.ascontiguousarray(A["fwd_in"]), np.ascontiguousarray(A["inv_in"])
+    for two in (0, 1):
+        got = np.zeros_like(A["fwd_out"])
+        assert L.AecmB200_SelfTestFftForward(vp(fwd), vp(got), len(fwd), two) == 0
+        np.testing.assert_array_equal(got, A["fwd_out"])
+    got, sc = np.zeros_like(A["inv_out"]), np.zeros(len(inv), dtype=np.int32)
+    assert L.AecmB200_SelfTestFftInverse(vp(inv), vp(got), vp(sc), len(inv)) == 0
+    np.testing.assert_array_equal(sc, A["inv_scale"])
+    np.testing.assert_array_equal(got, A["inv_out"])
 
 
 @pytest.mark.parametrize("adjacent,all_slots", [(False, False), (True, False), (True, True)],
@@ -369,7 +435,69 @@ def test_instance_index_scatters_rows_over_the_batch():
     bad[5] = total  # out of range
     a = api.StreamArgs(far.ctypes.data, near.ctypes.data, None, out.ctypes.data, calls * spc, 0, n, spc, 1, None, 40, None, None, bad.ctypes.data)
     assert L.AecmB200_ProcessStream(b._h, C.byref(a)) == 12004
+    dup = index.copy()
+    dup[7] = dup[2]  # two rows naming one instance would be two warps racing on one record: rejected up front
+    a = api.StreamArgs(far.ctypes.data, near.ctypes.data, None, out.ctypes.data, calls * spc, 0, n, spc, 1, None, 40, None, None, dup.ctypes.data)
+    assert L.AecmB200_SubmitStream(b._h, C.byref(a), 1) == 12004
+    assert L.AecmB200_WaitStream(b._h, 1) == 0  # the refused submission left its slot free ...
+    a = api.StreamArgs(far.ctypes.data, near.ctypes.data, None, out.ctypes.data, calls * spc, 0, n, spc, 1, None, 40, None,
+                       status.ctypes.data, index.ctypes.data)
+    assert L.AecmB200_SubmitStream(b._h, C.byref(a), 1) == 0  # ... so it takes the next one
+    assert L.AecmB200_SubmitStream(b._h, C.byref(a), 1) == 12004  # and is busy until waited for
+    assert L.AecmB200_WaitStream(b._h, 1) == 0 and not status.any()
     b.close()
+
+
+def test_group_on_distinct_devices_and_callers_device_is_left_alone():
+    """AecmB200_Group* with one shard per visible GPU (needs >= 2): every shard's batch sits on its own device, the sharded
+    result equals the oracle, and no library call leaves the calling thread on another CUDA device than it found."""
+    import ctypes as C
+
+    import torch
+
+    from webrtc_aecm_b200 import api
+
+    L = api.lib()
+    ndev = L.AecmB200_DeviceCount()
+    if ndev < 2:
+        pytest.skip("one GPU visible: distinct-device sharding needs two")
+    fs, spc, calls = 16000, 160, 50
+    n = 64 * ndev + 3
+    far, near = synth_streams(n, calls * spc, fs, seed=8, delay_ms=np.arange(n) % 90)
+    want, _, _ = ol.run_streams(far, near, fs=fs, impl="oracle")
+    home = ndev - 1
+    torch.cuda.set_device(home)
+    g = L.AecmB200_GroupCreate(n, ndev, None)
+    assert g and torch.cuda.current_device() == home
+    f0, c0 = C.c_int32(), C.c_int32()
+    devices = []
+    for i in range(ndev):
+        h = L.AecmB200_GroupShard(g, i, C.byref(f0), C.byref(c0))
+        devices.append(L.AecmB200_Device(h))
+    assert devices == list(range(ndev))
+    assert L.AecmB200_GroupInit(g, fs) == 0 and torch.cuda.current_device() == home
+    st = np.zeros(n, dtype=np.int32)
+    assert L.AecmB200_GroupSetConfig(g, api.AecmConfig(1, 3), st.ctypes.data) == 0 and not st.any()
+    out = np.zeros_like(near)
+    S = L.AecmB200_NumStreamSlots()
+    fuse = 5
+    chunks = [(np.ascontiguousarray(far[:, c * spc:(c + fuse) * spc]), np.ascontiguousarray(near[:, c * spc:(c + fuse) * spc]),
+               np.zeros((n, fuse * spc), dtype=np.int16)) for c in range(0, calls, fuse)]
+    for k, (f, nr, o) in enumerate(chunks):  # pipelined over the slots, every shard working on its slice
+        if k >= S:
+            assert L.AecmB200_GroupWaitStream(g, k % S) == 0
+        a = api.StreamArgs(f.ctypes.data, nr.ctypes.data, None, o.ctypes.data, fuse * spc, 0, n, spc, fuse, None, 40, None, st.ctypes.data)
+        assert L.AecmB200_GroupSubmitStream(g, C.byref(a), k % S) == 0
+        assert torch.cuda.current_device() == home
+    for s_ in range(S):
+        assert L.AecmB200_GroupWaitStream(g, s_) == 0
+    assert not st.any()
+    for k, (_, _, o) in enumerate(chunks):
+        out[:, k * fuse * spc:(k + 1) * fuse * spc] = o
+    np.testing.assert_array_equal(out, want)
+    L.AecmB200_GroupFree(g)
+    assert torch.cuda.current_device() == home
+    torch.cuda.set_device(0)
 
 
 def test_group_sharding_over_devices_matches_oracle():

@@ -273,3 +273,32 @@ def test_live_config_and_echo_path_changes_mid_stream():
     np.testing.assert_array_equal(got, wantp)
     L.WebRtcAecm_Free(h)
     o.close()
+
+
+def test_pools_come_and_go_with_their_handles():
+    """256 handles share a pool (a device batch + pinned planes).  300 handles need two pools; freeing all of them must
+    release the second pool (only one empty pool is kept for cheap Create/Free cycles) and later handles must start from a
+    clean, un-initialised instance again -- and still cancel echo bit-exactly."""
+    from webrtc_aecm_b200 import api
+
+    L = api.scalar_api()
+    fs, spc, calls = 16000, 160, 30
+    far, near = synth_streams(2, calls * spc, fs, seed=99, delay_ms=20)
+    want, _, _ = ol.run_streams(far, near, fs=fs, impl="oracle")
+    for round_ in range(2):
+        hs = [L.WebRtcAecm_Create() for _ in range(300)]
+        assert all(hs) and len(set(hs)) == 300
+        out = np.zeros(spc, dtype=np.int16)
+        # a recycled slot is a fresh instance: un-initialised until Init
+        assert L.WebRtcAecm_Process(hs[299], P(near[0, :spc].copy()), None, P(out), spc, 40) == api.AECM_UNINITIALIZED_ERROR
+        got = np.zeros_like(near)
+        for k, h in enumerate((hs[3], hs[290])):  # one handle of each pool
+            assert L.WebRtcAecm_Init(h, fs) == 0
+            for c in range(calls):
+                f = np.ascontiguousarray(far[k, c * spc:(c + 1) * spc])
+                n = np.ascontiguousarray(near[k, c * spc:(c + 1) * spc])
+                assert L.WebRtcAecm_BufferFarend(h, P(f), spc) == 0
+                assert L.WebRtcAecm_Process(h, P(n), None, P(got[k, c * spc:(c + 1) * spc]), spc, 40) == 0
+        np.testing.assert_array_equal(got, want)
+        for h in hs:
+            L.WebRtcAecm_Free(h)

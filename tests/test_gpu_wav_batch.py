@@ -84,3 +84,24 @@ def test_echo_mode_and_ms_options_reach_the_instances(tmp_path):
     for i in range(3):
         got = np.frombuffer(open(tmp_path / f"near{i}_out.wav", "rb").read()[44:], dtype="<i2")
         np.testing.assert_array_equal(got, want[i])
+
+
+def test_one_unreadable_pair_costs_only_its_own_output(tmp_path):
+    """Per-pair semantics, as in the reference CLI (which simply skips a pair it cannot read): a junk file among good
+    pairs must not withhold the good pairs' outputs.  The tool still exits 1 and names what was lost."""
+    pairs = make_pairs(tmp_path, 4, seed=9)
+    want = reference_outputs(pairs, tmp_path)
+    (tmp_path / "junk_far.wav").write_bytes(b"this is not a RIFF file")
+    (tmp_path / "junk_near.wav").write_bytes(b"RIFF\x00\x00\x00\x00nope")
+    args = []
+    for d in pairs[:2]:
+        args += [str(d / "far.wav"), str(d / "near.wav")]
+    args += [str(tmp_path / "junk_far.wav"), str(tmp_path / "junk_near.wav")]
+    for d in pairs[2:]:
+        args += [str(d / "far.wav"), str(d / "near.wav")]
+    res = subprocess.run([TOOL, *args], capture_output=True, text=True, timeout=300)
+    assert res.returncode == 1, (res.stdout, res.stderr)
+    assert "1 pair(s) unreadable" in res.stderr and "4 pairs written" in res.stdout
+    assert not (tmp_path / "junk_near_out.wav").exists()
+    for d in pairs:
+        assert open(d / "near_out.wav", "rb").read() == want[d.name], d.name

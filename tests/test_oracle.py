@@ -66,6 +66,28 @@ def test_fft_inverse_known_answers_and_scale():
     assert len(set(iscale.tolist())) >= 4 and iscale.min() == 0  # the vectors exercise the block-floating scaling
 
 
+def test_fft_adversarial_family_known_answers():
+    """The oracle's FFT/IFFT on the larger adversarial family (tests/cases.py:fft_adversarial_vectors), against the
+    reference's answers in tests/golden/fft_adversarial.npz; and the committed inputs are what cases.py generates."""
+    from cases import fft_adversarial_vectors
+
+    lib = ol.oracle()
+    A = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "fft_adversarial.npz"))
+    fwd, inv = fft_adversarial_vectors()
+    np.testing.assert_array_equal(fwd, A["fwd_in"])
+    np.testing.assert_array_equal(inv, A["inv_in"])
+    got = np.zeros_like(A["fwd_out"])
+    for i in range(len(fwd)):
+        lib.oracle_real_fft128_forward(fwd[i].ctypes.data_as(C.c_void_p), got[i].ctypes.data_as(C.c_void_p))
+    np.testing.assert_array_equal(got, A["fwd_out"])
+    got, sc = np.zeros_like(A["inv_out"]), np.zeros(len(inv), dtype=np.int32)
+    for i in range(len(inv)):
+        sc[i] = lib.oracle_real_fft128_inverse(inv[i].ctypes.data_as(C.c_void_p), got[i].ctypes.data_as(C.c_void_p))
+    np.testing.assert_array_equal(sc, A["inv_scale"])
+    np.testing.assert_array_equal(got, A["inv_out"])
+    assert set(A["inv_scale"].tolist()) >= {0, 1, 2, 3, 4}
+
+
 def test_sqrt_floor_and_lcg_known_answers():
     lib = ol.oracle()
     got = np.array([lib.oracle_sqrt_floor(int(v)) for v in VEC["sqrt_in"]], dtype=np.int32)

@@ -5,6 +5,7 @@ Run in the build container (needs /root/reference to have been compiled by oracl
     python tools/make_golden.py
 Writes
     tests/golden/streams.json   per case: sha256 of the reference's int16 output + OR of its return codes
+    tests/golden/fft_adversarial.npz  a larger adversarial FFT/IFFT family with the reference's answers
     tests/golden/vectors.npz    full reference outputs for two small cases, and stage-level known-answer
                                 vectors produced by the reference's own C symbols (forward/inverse real FFT
                                 incl. the returned scale, WebRtcSpl_SqrtFloor, WebRtcSpl_RandUArray)
@@ -23,7 +24,7 @@ sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 import oracle_lib as ol  # noqa: E402
-from cases import CASES, make_inputs, run_kwargs  # noqa: E402
+from cases import CASES, fft_adversarial_vectors, make_inputs, run_kwargs  # noqa: E402
 from webrtc_aecm_b200.shard import stream_checksum  # noqa: E402
 
 FULL_VECTOR_CASES = ("16k_80_sample_calls", "16k_full_scale_alternating")
@@ -57,6 +58,19 @@ def stage_vectors(ref):
         buf = np.zeros(260, dtype=np.int16)  # the reference reads n+2 and may be handed a larger buffer
         buf[:130] = iin[i]
         iscale[i] = ref.WebRtcSpl_RealInverseFFT(fft, buf.ctypes.data, iout[i].ctypes.data)
+    # a second, larger adversarial family (tests/cases.py), kept in its own file
+    afwd, ainv = fft_adversarial_vectors()
+    afout = np.zeros((len(afwd), 130), dtype=np.int16)
+    for i in range(len(afwd)):
+        ref.WebRtcSpl_RealForwardFFT(fft, afwd[i].ctypes.data, afout[i].ctypes.data)
+    aiout = np.zeros((len(ainv), 128), dtype=np.int16)
+    aiscale = np.zeros(len(ainv), dtype=np.int32)
+    for i in range(len(ainv)):
+        buf = np.zeros(260, dtype=np.int16)
+        buf[:130] = ainv[i]
+        aiscale[i] = ref.WebRtcSpl_RealInverseFFT(fft, buf.ctypes.data, aiout[i].ctypes.data)
+    np.savez_compressed(os.path.join(ROOT, "tests", "golden", "fft_adversarial.npz"), fwd_in=afwd, fwd_out=afout, inv_in=ainv,
+                        inv_out=aiout, inv_scale=aiscale)
     sq_in = np.concatenate([np.arange(0, 70), (np.arange(1, 46341, 97) ** 2), (np.arange(2, 46341, 89) ** 2) - 1,
                             (np.arange(1, 46340, 83) ** 2) + 1, [2**31 - 1, 2**30, -1, -2**31],
                             rng.integers(0, 2**31, size=500)]).astype(np.int64)

@@ -103,6 +103,7 @@ def lib():
             "AecmB200_AdoptCudaStream": (i32, [vp, vp]),
             "AecmB200_HostAlloc": (vp, [C.c_size_t]), "AecmB200_HostFree": (None, [vp]),
             "AecmB200_SelfTestSqrtFloor": (C.c_int64, [C.c_uint32, C.c_uint32]), "AecmB200_NumStreamSlots": (i32, []),
+            "AecmB200_SelfTestFftForward": (i32, [vp, vp, i32, i32]), "AecmB200_SelfTestFftInverse": (i32, [vp, vp, vp, i32]),
             "AecmB200_ScalarApiStats": (None, [vp, C.POINTER(i64), C.POINTER(i64)]),
             "AecmB200_StateBytes": (C.c_size_t, []), "AecmB200_ReadState": (i32, [vp, i32, vp, C.c_size_t]),
             "AecmB200_KernelLaunchCount": (i64, []), "AecmB200_DeviceCount": (i32, []),

@@ -46,6 +46,7 @@ struct AecmB200Batch {
     int trace;
     int32_t *d_status;      /* scratch for the control calls (set_config, echo path) */
     int16_t *d_path;
+    uint64_t *index_seen;   /* bitmap over the instances, for the duplicate check of instanceIndex (allocated on first use) */
     char err[256];
 };
 
@@ -61,6 +62,23 @@ static int fail(AecmB200Batch *b, const char *what, cudaError_t e) {
         if (e_ != cudaSuccess) return fail((b), #call, e_); \
     } while (0)
 
+/* Every entry point makes the batch's device current for its own CUDA calls and puts the caller's device back on the way
+ * out (all return paths: the scope object's cleanup handler runs when the function leaves), so a host application that
+ * uses CUDA on another device is not silently switched. */
+typedef struct { int prev; } DeviceScope;
+static void device_scope_exit(DeviceScope *s) {
+    if (s->prev >= 0) cudaSetDevice(s->prev);
+}
+static cudaError_t device_scope_enter(DeviceScope *s, int device) {
+    int cur = -1;
+    if (cudaGetDevice(&cur) == cudaSuccess && cur == device) return cudaSuccess; /* already there: nothing to restore */
+    s->prev = cur;
+    return cudaSetDevice(device);
+}
+#define ENTER_DEVICE(b)                                                           \
+    DeviceScope scope_ __attribute__((cleanup(device_scope_exit))) = {-1};        \
+    CU((b), device_scope_enter(&scope_, (b)->device))
+
 int32_t AecmB200_DeviceCount(void) {
     int n = 0;
     if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
@@ -69,8 +87,9 @@ int32_t AecmB200_DeviceCount(void) {
 
 AecmB200Batch *AecmB200_Create(int32_t n, int32_t device) {
     AecmB200Batch *b;
+    DeviceScope scope_ __attribute__((cleanup(device_scope_exit))) = {-1};
     if (n <= 0) return NULL;
-    if (cudaSetDevice(device) != cudaSuccess) {
+    if (device_scope_enter(&scope_, device) != cudaSuccess) {
         fprintf(stderr, "aecm_b200: CUDA device %d unavailable (%s); this library has no CPU path\n", device,
                 cudaGetErrorString(cudaGetLastError()));
         return NULL;
@@ -123,8 +142,9 @@ AecmB200Batch *AecmB200_Create(int32_t n, int32_t device) {
 }
 
 void AecmB200_Free(AecmB200Batch *b) {
+    DeviceScope scope_ __attribute__((cleanup(device_scope_exit))) = {-1};
     if (!b) return;
-    cudaSetDevice(b->device);
+    device_scope_enter(&scope_, b->device);
     if (b->stream) cudaStreamSynchronize(b->stream);
     cudaFree(b->planes.state);
     cudaFree(b->planes.far_hist);
@@ -145,6 +165,7 @@ void AecmB200_Free(AecmB200Batch *b) {
     cudaFree(b->d_status);
     cudaFree(b->d_path);
     if (b->stream && b->owns_stream) cudaStreamDestroy(b->stream);
+    free(b->index_seen);
     free(b);
 }
 
@@ -155,7 +176,7 @@ void *AecmB200_CudaStream(const AecmB200Batch *b) { return b ? (void *)b->stream
 
 int32_t AecmB200_AdoptCudaStream(AecmB200Batch *b, void *s) {
     if (!b) return -1;
-    CU(b, cudaSetDevice(b->device));
+    ENTER_DEVICE(b);
     CU(b, cudaStreamSynchronize(b->stream));
     if (b->owns_stream) cudaStreamDestroy(b->stream);
     b->stream = (cudaStream_t)s;
@@ -165,7 +186,7 @@ int32_t AecmB200_AdoptCudaStream(AecmB200Batch *b, void *s) {
 
 int32_t AecmB200_Synchronize(AecmB200Batch *b) {
     if (!b) return -1;
-    CU(b, cudaSetDevice(b->device));
+    ENTER_DEVICE(b);
     if (use_main_stream(b)) return AECM_UNSPECIFIED_ERROR;
     CU(b, cudaStreamSynchronize(b->stream));
     return 0;
@@ -184,6 +205,16 @@ size_t AecmB200_StateBytes(void) { return sizeof(AecmInstanceState); }
 int64_t AecmB200_KernelLaunchCount(void) { return aecm_cuda_kernel_launch_count(); }
 int32_t AecmB200_NumStreamSlots(void) { return AECM_SLOTS; }
 int64_t AecmB200_SelfTestSqrtFloor(uint32_t first, uint32_t count) { return aecm_cuda_selftest_sqrt(first, count); }
+int32_t AecmB200_SelfTestFftForward(const int16_t *in, int16_t *out, int32_t n, int32_t twoSignals) {
+    if (!in || !out) return AECM_NULL_POINTER_ERROR;
+    if (n < 0) return AECM_BAD_PARAMETER_ERROR;
+    return aecm_cuda_selftest_fft(twoSignals ? 1 : 0, in, out, NULL, n) == 0 ? 0 : AECM_UNSPECIFIED_ERROR;
+}
+int32_t AecmB200_SelfTestFftInverse(const int16_t *in, int16_t *out, int32_t *scale, int32_t n) {
+    if (!in || !out || !scale) return AECM_NULL_POINTER_ERROR;
+    if (n < 0) return AECM_BAD_PARAMETER_ERROR;
+    return aecm_cuda_selftest_fft(2, in, out, scale, n) == 0 ? 0 : AECM_UNSPECIFIED_ERROR;
+}
 
 /* Called before enqueuing anything on the main stream: order it after the kernels of earlier submissions and
  * remember that later submissions have to follow it. */
@@ -204,7 +235,7 @@ int32_t AecmB200_ReadState(AecmB200Batch *b, int32_t instance, void *dst, size_t
     if (!b) return -1;
     if (!dst) return AECM_NULL_POINTER_ERROR;
     if (!range_ok(b, instance, 1) || bytes > sizeof(AecmInstanceState)) return AECM_BAD_PARAMETER_ERROR;
-    CU(b, cudaSetDevice(b->device));
+    ENTER_DEVICE(b);
     if (use_main_stream(b)) return AECM_UNSPECIFIED_ERROR;
     CU(b, cudaMemcpyAsync(dst, b->planes.state + instance, bytes, cudaMemcpyDeviceToHost, b->stream));
     CU(b, cudaStreamSynchronize(b->stream));
@@ -214,7 +245,7 @@ int32_t AecmB200_ReadState(AecmB200Batch *b, int32_t instance, void *dst, size_t
 int32_t AecmB200_Reset(AecmB200Batch *b, int32_t first, int32_t count) {
     if (!b) return -1;
     if (!range_ok(b, first, count)) return AECM_BAD_PARAMETER_ERROR;
-    CU(b, cudaSetDevice(b->device));
+    ENTER_DEVICE(b);
     if (use_main_stream(b)) return AECM_UNSPECIFIED_ERROR;
     CU(b, cudaMemsetAsync(b->planes.state + first, 0, (size_t)count * sizeof(AecmInstanceState), b->stream));
     CU(b, cudaStreamSynchronize(b->stream));
@@ -225,7 +256,7 @@ int32_t AecmB200_Init(AecmB200Batch *b, int32_t first, int32_t count, int32_t fs
     if (!b) return -1;
     if (fs != 8000 && fs != 16000) return AECM_BAD_PARAMETER_ERROR; /* echo_control_mobile.cc:150-152 */
     if (!range_ok(b, first, count)) return AECM_BAD_PARAMETER_ERROR;
-    CU(b, cudaSetDevice(b->device));
+    ENTER_DEVICE(b);
     if (use_main_stream(b)) return AECM_UNSPECIFIED_ERROR;
     CU(b, (cudaError_t)aecm_cuda_launch_init(&b->planes, first, count, fs, b->stream));
     return 0;
@@ -240,7 +271,7 @@ static int copy_status_out(AecmB200Batch *b, int32_t *status, int32_t count) {
 int32_t AecmB200_SetConfig(AecmB200Batch *b, int32_t first, int32_t count, AecmConfig cfg, int32_t *status) {
     if (!b) return -1;
     if (!range_ok(b, first, count)) return AECM_BAD_PARAMETER_ERROR;
-    CU(b, cudaSetDevice(b->device));
+    ENTER_DEVICE(b);
     if (use_main_stream(b)) return AECM_UNSPECIFIED_ERROR;
     CU(b, (cudaError_t)aecm_cuda_launch_set_config(&b->planes, first, count, cfg.cngMode, cfg.echoMode, b->d_status, b->stream));
     return copy_status_out(b, status, count);
@@ -254,7 +285,7 @@ int32_t AecmB200_InitEchoPath(AecmB200Batch *b, int32_t instance, const void *pa
     if (!path) return AECM_NULL_POINTER_ERROR;
     if (size_bytes != WebRtcAecm_echo_path_size_bytes()) return AECM_BAD_PARAMETER_ERROR;
     if (!range_ok(b, instance, 1)) return AECM_BAD_PARAMETER_ERROR;
-    CU(b, cudaSetDevice(b->device));
+    ENTER_DEVICE(b);
     if (use_main_stream(b)) return AECM_UNSPECIFIED_ERROR;
     CU(b, cudaMemcpyAsync(b->d_path, path, size_bytes, cudaMemcpyHostToDevice, b->stream));
     CU(b, (cudaError_t)aecm_cuda_launch_init_echo_path(&b->planes, instance, 1, b->d_path, AECM_BINS, b->d_status, b->stream));
@@ -269,7 +300,7 @@ int32_t AecmB200_GetEchoPath(AecmB200Batch *b, int32_t instance, void *path, siz
     if (!path) return AECM_NULL_POINTER_ERROR;
     if (size_bytes != WebRtcAecm_echo_path_size_bytes()) return AECM_BAD_PARAMETER_ERROR;
     if (!range_ok(b, instance, 1)) return AECM_BAD_PARAMETER_ERROR;
-    CU(b, cudaSetDevice(b->device));
+    ENTER_DEVICE(b);
     if (use_main_stream(b)) return AECM_UNSPECIFIED_ERROR;
     base = (const char *)(b->planes.state + instance);
     CU(b, cudaMemcpyAsync(&flag, base + offsetof(AecmInstanceState, s) + offsetof(AecmScalars, init_flag), sizeof(flag),
@@ -318,7 +349,7 @@ int32_t AecmB200_ProcessStreamDevice(AecmB200Batch *b, const AecmB200StreamArgs 
     rc = validate_stream_args(b, a);
     if (rc) return rc;
     if (a->count == 0) return 0;
-    CU(b, cudaSetDevice(b->device));
+    ENTER_DEVICE(b);
     if (use_main_stream(b)) return AECM_UNSPECIFIED_ERROR;
     fill_call_args(&k, a);
     CU(b, (cudaError_t)aecm_cuda_launch_call(&b->planes, &k, b->stream));
@@ -351,28 +382,61 @@ static cudaError_t copy_plane(void *dst, size_t dpitch, const void *src, size_t 
 /* Host planes, asynchronous.  H2D on the slot's copy stream, the kernel on the batch's compute stream (so kernels of
  * successive submissions run in order: every call depends on the state left by the previous one), D2H back on the
  * copy stream.  With two slots the copies of call k+1 overlap the kernel of call k. */
+static int32_t enqueue_stream(AecmB200Batch *b, const AecmB200StreamArgs *h, Slot *sl);
+
+/* rows must name distinct instances: two warps working on one record would race (a host array here; the device array of
+ * AecmB200_ProcessStreamDevice is the caller's responsibility, the kernel only range-checks it) */
+static int32_t check_instance_index(AecmB200Batch *b, const int32_t *index, int32_t count) {
+    const size_t words = ((size_t)b->n + 63) / 64;
+    int32_t r, rc = 0;
+    if (!b->index_seen) {
+        b->index_seen = (uint64_t *)malloc(words * sizeof(uint64_t));
+        if (!b->index_seen) return AECM_UNSPECIFIED_ERROR;
+    }
+    memset(b->index_seen, 0, words * sizeof(uint64_t));
+    for (r = 0; r < count && !rc; r++) {
+        const int32_t i = index[r];
+        if (i < 0 || i >= b->n) rc = AECM_BAD_PARAMETER_ERROR;
+        else if (b->index_seen[i >> 6] & (1ull << (i & 63))) rc = AECM_BAD_PARAMETER_ERROR; /* duplicate */
+        else b->index_seen[i >> 6] |= 1ull << (i & 63);
+    }
+    return rc;
+}
+
 int32_t AecmB200_SubmitStream(AecmB200Batch *b, const AecmB200StreamArgs *h, int32_t slot) {
-    size_t width, rows, pitch_src, pitch_dst;
-    AecmCallArgs k;
     Slot *sl;
     int32_t rc;
-    int adjacent;
     if (!b) return -1;
     if (slot < 0 || slot >= AECM_SLOTS) return AECM_BAD_PARAMETER_ERROR;
     rc = validate_stream_args(b, h);
     if (rc) return rc;
-    if (h->instanceIndex) { /* a host array here (a device array in AecmB200_ProcessStreamDevice, checked by the kernel) */
-        int32_t r;
-        for (r = 0; r < h->count; r++)
-            if (h->instanceIndex[r] < 0 || h->instanceIndex[r] >= b->n) return AECM_BAD_PARAMETER_ERROR;
+    if (h->instanceIndex) {
+        rc = check_instance_index(b, h->instanceIndex, h->count);
+        if (rc) return rc;
     }
     sl = &b->slot[slot];
     if (sl->busy) return AECM_BAD_PARAMETER_ERROR; /* the previous submission on this slot was not waited for */
-    CU(b, cudaSetDevice(b->device));
-    sl->user_status = h->status;
-    sl->count = h->count;
-    sl->busy = 1;
-    if (h->count == 0) return 0;
+    ENTER_DEVICE(b);
+    sl->user_status = NULL;
+    sl->count = 0;
+    if (h->count > 0) {
+        rc = enqueue_stream(b, h, sl);
+        if (rc) { /* nothing of a failed submission may linger: drain what was enqueued, leave the slot free */
+            cudaStreamSynchronize(sl->copy);
+            return rc;
+        }
+        sl->user_status = h->status;
+        sl->count = h->count;
+    }
+    sl->busy = 1; /* only a fully enqueued submission occupies the slot */
+    return 0;
+}
+
+static int32_t enqueue_stream(AecmB200Batch *b, const AecmB200StreamArgs *h, Slot *sl) {
+    size_t width, rows, pitch_src, pitch_dst;
+    AecmCallArgs k;
+    int32_t rc;
+    int adjacent;
     width = (size_t)h->nCalls * (size_t)h->nrOfSamples; /* samples actually used per row */
     rows = (size_t)h->count;
     rc = grow_planes(b, sl, rows * width, h->nearendClean != NULL);
@@ -459,7 +523,7 @@ int32_t AecmB200_WaitStream(AecmB200Batch *b, int32_t slot) {
     if (slot < 0 || slot >= AECM_SLOTS) return AECM_BAD_PARAMETER_ERROR;
     sl = &b->slot[slot];
     if (!sl->busy) return 0;
-    CU(b, cudaSetDevice(b->device));
+    ENTER_DEVICE(b);
     CU(b, cudaStreamSynchronize(sl->copy));
     if (b->trace && sl->count > 0) {
         float h2d = 0, gap = 0, ker = 0, d2h = 0;
@@ -480,11 +544,8 @@ int32_t AecmB200_ProcessStream(AecmB200Batch *b, const AecmB200StreamArgs *h) {
     if (!b) return -1;
     rc = AecmB200_WaitStream(b, 0); /* keep submission order if the caller mixes the two styles */
     if (rc) return rc;
-    rc = AecmB200_SubmitStream(b, h, 0);
-    if (rc) {
-        b->slot[0].busy = 0;
-        return rc;
-    }
+    rc = AecmB200_SubmitStream(b, h, 0); /* a failed submission leaves the slot free */
+    if (rc) return rc;
     return AecmB200_WaitStream(b, 0);
 }
 

@@ -262,6 +262,66 @@ __global__ void aecm_sqrt_selftest_kernel(uint32_t first, uint32_t count, unsign
     if (mine) atomicAdd(bad, mine);
 }
 
+// Known-answer harness for the warp FFT exactly as aecm_call_kernel uses it (same tables, same tile layout, same
+// bin -> lane mapping): one warp per vector.  mode 0: forward128<1>, 1: forward128<2> on vectors (2v, 2v+1), 2: inverse128
+// with the conjugate-symmetric fill and the peak scan of process_block.  in/out are device arrays:
+//   forward  in [n][128] windowed real samples   out [n][130] bins 0..64 interleaved re,im (before the sign flip)
+//   inverse  in [n][130] bins 0..64 interleaved  out [n][128] real samples, scale[n] the accumulated block-floating shift
+__global__ void aecm_fft_selftest_kernel(int mode, const int16_t *in, int16_t *out, int32_t *scale, int n) {
+    __shared__ __align__(16) uint32_t tiles[4][256];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    uint32_t *tile = tiles[warp];
+    const int v = (blockIdx.x * 4 + warp) * (mode == 1 ? 2 : 1);
+    if (v >= n) return;
+    const int4 lwv = __ldg(&kLaneTables.words[lane]);
+    const aecm_fft::LaneWords lw{lwv.x, lwv.y, lwv.z, lwv.w};
+    const int n0 = (int)(__brev((unsigned)lane) >> 27);
+    if (mode == 0) {
+        int x[1][4], re[1][3], im[1][3];
+        for (int k = 0; k < 4; k++) x[0][k] = in[(size_t)v * 128 + n0 + 32 * k];
+        aecm_fft::forward128<1>(x, tile, twiddle_table(), lw, lane, re, im);
+        for (int p = 0; p < 3; p++) {
+            const int bin = p < 2 ? lane + 32 * p : 64;
+            if (p < 2 || lane == 0) {
+                out[(size_t)v * 130 + 2 * bin] = (int16_t)re[0][p];
+                out[(size_t)v * 130 + 2 * bin + 1] = (int16_t)im[0][p];
+            }
+        }
+    } else if (mode == 1) {
+        int x[2][4], re[2][3], im[2][3];
+        for (int s = 0; s < 2; s++)
+            for (int k = 0; k < 4; k++) x[s][k] = in[(size_t)min(v + s, n - 1) * 128 + n0 + 32 * k];
+        aecm_fft::forward128<2>(x, tile, twiddle_table(), lw, lane, re, im);
+        for (int s = 0; s < 2 && v + s < n; s++)
+            for (int p = 0; p < 3; p++) {
+                const int bin = p < 2 ? lane + 32 * p : 64;
+                if (p < 2 || lane == 0) {
+                    out[(size_t)(v + s) * 130 + 2 * bin] = (int16_t)re[s][p];
+                    out[(size_t)(v + s) * 130 + 2 * bin + 1] = (int16_t)im[s][p];
+                }
+            }
+    } else {
+        const int4 lb = __ldg(&kLaneTables.bins[lane]);
+        const int words[2] = {lb.x, lb.y}, mirrors[2] = {lb.z, lb.w};
+        int peak = 0;
+        for (int p = 0; p < 3; p++) {
+            const int i = p < 2 ? lane + 32 * p : 64;
+            if (p < 2 || lane == 0) {
+                const int re = in[(size_t)v * 130 + 2 * i], im = in[(size_t)v * 130 + 2 * i + 1];
+                tile[p < 2 ? words[p] : aecm_fft::phys(1)] = pack16(re, im);
+                peak = max(peak, max(abs(re), abs(im)));
+                if (p < 2 && i > 0) tile[mirrors[p]] = pack16(re, s16(-im));  // real_fft.c:87-91
+            }
+        }
+        peak = min(__reduce_max_sync(kFull, peak), 32767);
+        __syncwarp();
+        int td[4];
+        const int sc = aecm_fft::inverse128(tile, twiddle_table(), lw, lane, peak, td);
+        for (int k = 0; k < 4; k++) out[(size_t)v * 128 + lane + 32 * k] = (int16_t)td[k];
+        if (lane == 0) scale[v] = sc;
+    }
+}
+
 extern "C" {
 
 int aecm_cuda_kernel_launch_count(void) { return g_launches.load(); }
@@ -335,6 +395,32 @@ long long aecm_cuda_selftest_sqrt(uint32_t first, uint32_t count) {
     cudaError_t e = cudaMemcpy(&bad, d_bad, sizeof(bad), cudaMemcpyDeviceToHost);
     cudaFree(d_bad);
     return e == cudaSuccess ? (long long)bad : -(long long)e;
+}
+
+// diagnostics: the kernel's warp FFT on host vectors (see aecm_fft_selftest_kernel); returns a cudaError_t value
+int aecm_cuda_selftest_fft(int mode, const int16_t *in, int16_t *out, int32_t *scale, int n) {
+    if (n <= 0) return 0;
+    const size_t in_w = mode == 2 ? 130 : 128, out_w = mode == 2 ? 128 : 130;
+    int16_t *d_in = nullptr, *d_out = nullptr;
+    int32_t *d_scale = nullptr;
+    cudaError_t e = cudaMalloc(&d_in, (size_t)n * in_w * sizeof(int16_t));
+    if (e == cudaSuccess) e = cudaMalloc(&d_out, (size_t)n * out_w * sizeof(int16_t));
+    if (e == cudaSuccess) e = cudaMalloc(&d_scale, (size_t)n * sizeof(int32_t));
+    if (e == cudaSuccess) e = cudaMemcpy(d_in, in, (size_t)n * in_w * sizeof(int16_t), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemset(d_out, 0, (size_t)n * out_w * sizeof(int16_t));
+    if (e == cudaSuccess) e = cudaMemset(d_scale, 0, (size_t)n * sizeof(int32_t));
+    if (e == cudaSuccess) {
+        const int vectors_per_block = mode == 1 ? 8 : 4;
+        aecm_fft_selftest_kernel<<<(n + vectors_per_block - 1) / vectors_per_block, 128>>>(mode, d_in, d_out, d_scale, n);
+        g_launches++;
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = cudaMemcpy(out, d_out, (size_t)n * out_w * sizeof(int16_t), cudaMemcpyDeviceToHost);
+    if (e == cudaSuccess && scale) e = cudaMemcpy(scale, d_scale, (size_t)n * sizeof(int32_t), cudaMemcpyDeviceToHost);
+    cudaFree(d_in);
+    cudaFree(d_out);
+    cudaFree(d_scale);
+    return (int)e;
 }
 
 }  // extern "C"

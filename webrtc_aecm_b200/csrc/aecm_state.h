@@ -158,6 +158,7 @@ int aecm_cuda_launch_init_echo_path(const AecmBatchPlanes *p, int first, int cou
                                     int path_stride, int32_t *status, void *stream);
 int aecm_cuda_launch_call(const AecmBatchPlanes *p, const AecmCallArgs *a, void *stream);
 long long aecm_cuda_selftest_sqrt(uint32_t first, uint32_t count);
+int aecm_cuda_selftest_fft(int mode, const int16_t *in, int16_t *out, int32_t *scale, int n); /* host arrays */
 int aecm_cuda_kernel_launch_count(void); /* kernels launched so far by this translation unit */
 
 #ifdef __cplusplus

@@ -417,7 +417,7 @@ static void add_pair(Pair **v, int *n, int *cap, const char *far, const char *ne
 int main(int argc, char **argv) {
     Options o;
     Pair *pairs = NULL;
-    int n = 0, cap = 0, i, d, bad = 0, written = 0, skipped = 0, unsupported = 0;
+    int n = 0, cap = 0, i, d, bad = 0, read_bad = 0, proc_bad = 0, written = 0, skipped = 0, unsupported = 0;
     const char *lists[64];
     int n_lists = 0;
     double t0, t_read, t_proc, t_write, t_init = 0;
@@ -470,8 +470,8 @@ int main(int argc, char **argv) {
 
     t0 = now_s();
     run_io(pairs, n, o.io_threads, o.quiet, 0);
-    for (i = 0; i < n; i++) {
-        bad += pairs[i].failed;
+    for (i = 0; i < n; i++) { /* an unreadable / non-WAV input costs its own pair only (the reference CLI skips it the same way) */
+        read_bad += pairs[i].failed;
         unsupported += pairs[i].unsupported;
     }
     t_read = now_s() - t0;
@@ -500,7 +500,13 @@ int main(int argc, char **argv) {
             for (d = 0; d < o.n_devices; d++) pthread_create(&th[d], NULL, run_shard, &shards[d]);
             for (d = 0; d < o.n_devices; d++) {
                 pthread_join(th[d], NULL);
-                if (shards[d].failed) { fprintf(stderr, "error (device %d): %s\n", shards[d].device, shards[d].err); bad++; }
+                if (shards[d].failed) { /* only the pairs of THIS shard lose their output; every other pair is still written */
+                    int j;
+                    fprintf(stderr, "error (device %d): %s; %d pair(s) of this shard get no output\n", shards[d].device, shards[d].err,
+                            shards[d].n);
+                    for (j = 0; j < shards[d].n; j++) shards[d].pairs[j]->skip = 1;
+                    proc_bad += shards[d].n;
+                }
                 blocks += shards[d].blocks_done;
                 if (shards[d].init_s > t_init) t_init = shards[d].init_s;
                 launches += shards[d].launches;
@@ -508,7 +514,6 @@ int main(int argc, char **argv) {
             }
             free(sel);
         }
-        if (bad) { fprintf(stderr, "aecm_wav_batch: processing failed, no output written\n"); return 1; }
     }
     t_proc = now_s() - t0;
 
@@ -530,5 +535,8 @@ int main(int argc, char **argv) {
                t_proc > t_init ? (double)blocks / (t_proc - t_init) : 0.0, t_proc > t_init ? audio_s / (t_proc - t_init) : 0.0, t_write);
     for (i = 0; i < n; i++) { free(pairs[i].far); free(pairs[i].near); free(pairs[i].far_path); free(pairs[i].near_path); free(pairs[i].out_path); }
     free(pairs);
-    return bad ? 1 : 0;
+    if (read_bad || proc_bad || bad)
+        fprintf(stderr, "aecm_wav_batch: %d pair(s) unreadable, %d lost to a failed device shard, %d not writable; the other %d were written\n",
+                read_bad, proc_bad, bad, written);
+    return (read_bad || proc_bad || bad) ? 1 : 0;
 }

@@ -75,9 +75,26 @@ typedef struct {
 static Pool *g_pools = NULL;
 static pthread_mutex_t g_lock = PTHREAD_MUTEX_INITIALIZER;
 
-static int default_device(void) {
+/* Device of the next pool: AECM_B200_DEVICE pins every pool to one GPU; otherwise pools are dealt round-robin over
+ * the visible GPUs (256 handles per pool), so a process with thousands of scalar handles uses the whole box. */
+static int g_pools_created = 0;
+static int next_pool_device(void) {
     const char *e = getenv("AECM_B200_DEVICE");
-    return e ? atoi(e) : 0;
+    int n;
+    if (e) return atoi(e);
+    n = AecmB200_DeviceCount();
+    return n > 0 ? g_pools_created % n : 0;
+}
+
+static void destroy_pool(Pool *p) { /* g_lock held; no handle of the pool is left, so nobody can be inside it */
+    Pool **pp;
+    for (pp = &g_pools; *pp && *pp != p; pp = &(*pp)->next) {}
+    if (*pp) *pp = p->next;
+    AecmB200_HostFree(p->h_far); AecmB200_HostFree(p->h_near); AecmB200_HostFree(p->h_clean); AecmB200_HostFree(p->h_out);
+    AecmB200_Free(p->batch);
+    pthread_mutex_destroy(&p->q_lock);
+    pthread_mutex_destroy(&p->exec);
+    free(p);
 }
 
 void *WebRtcAecm_Create(void) { /* echo_control_mobile.cc:89-117 */
@@ -90,7 +107,7 @@ void *WebRtcAecm_Create(void) { /* echo_control_mobile.cc:89-117 */
         p = (Pool *)calloc(1, sizeof(Pool));
         if (p) {
             const size_t plane = (size_t)POOL_SLOTS * MAX_SAMPLES * sizeof(int16_t);
-            p->batch = AecmB200_Create(POOL_SLOTS, default_device());
+            p->batch = AecmB200_Create(POOL_SLOTS, next_pool_device());
             if (p->batch) {
                 p->h_far = (int16_t *)AecmB200_HostAlloc(plane);
                 p->h_near = (int16_t *)AecmB200_HostAlloc(plane);
@@ -107,6 +124,7 @@ void *WebRtcAecm_Create(void) { /* echo_control_mobile.cc:89-117 */
                 pthread_mutex_init(&p->exec, NULL);
                 p->next = g_pools;
                 g_pools = p;
+                g_pools_created++;
             }
         }
     }
@@ -139,8 +157,11 @@ void WebRtcAecm_Free(void *inst) { /* echo_control_mobile.cc:119-140 */
     if (!h || h->magic != HANDLE_MAGIC) return;
     pthread_mutex_lock(&g_lock);
     h->pool->used[h->slot] = 0;
-    h->pool->n_used--;
     h->magic = 0;
+    /* the last handle of a pool takes the pool with it -- its 256-instance device batch, pinned planes, streams and
+     * events -- unless it is the only pool left: one empty pool is kept so that Create/Free cycles of a single handle
+     * (the reference CLI's pattern, main.cc:111 / :146) do not pay a device allocation each time */
+    if (--h->pool->n_used == 0 && (g_pools != h->pool || h->pool->next)) destroy_pool(h->pool);
     pthread_mutex_unlock(&g_lock);
     free(h);
 }
