@@ -304,11 +304,64 @@ static uint32_t binary_spectrum(const uint16_t *spec, int32_t *thr, int q, int32
 
 static uint32_t far_word(const OracleAecm *a, int delay) { return a->bin_far[(a->bin_far_head + delay) % OR_HIST]; }
 
-/* delay_estimator.cc:521-664 with robust validation off and lookahead 0 (aecm_core.cc:218,225);
- * the float histogram never feeds last_delay in that configuration and is not modelled. */
+/* UpdateRobustValidationStatistics, delay_estimator.cc:96-154.  Single-precision arithmetic, one rounding per
+ * operation, in the reference's order (the library is built without FMA contraction). */
+static void update_robust_statistics(OracleAecm *a, int cand, int32_t depth_q14, int32_t level_q14) {
+    const float q14 = 1.f / (1 << 14);
+    const float depth = depth_q14 * q14;
+    float decrease_in_last_set = depth;
+    const int max_hits_for_slow_change = cand < a->last_delay ? 10 : 1000; /* :101-103 */
+    int i;
+    if (cand != a->last_candidate_delay) { /* :108-111 */
+        a->candidate_hits = 0;
+        a->last_candidate_delay = cand;
+    }
+    a->candidate_hits++;
+    a->histogram[cand] += depth; /* :119-122 */
+    if (a->histogram[cand] > 3000.f) a->histogram[cand] = 3000.f;
+    if (a->candidate_hits < max_hits_for_slow_change) /* :132-136 */
+        decrease_in_last_set = (a->mean_bit_counts[a->compare_delay] - level_q14) * q14;
+    for (i = 0; i < OR_HIST; i++) { /* :140-153 */
+        const int in_last = i >= a->last_delay - 2 && i <= a->last_delay + 1 && i != cand;
+        const int in_cand = i >= cand - 2 && i <= cand + 1;
+        a->histogram[i] -= decrease_in_last_set * in_last + depth * (!in_last && !in_cand);
+        if (a->histogram[i] < 0) a->histogram[i] = 0;
+    }
+}
+
+static int histogram_based_validation(const OracleAecm *a, int cand) { /* delay_estimator.cc:178-225 */
+    float fraction = 1.f;
+    float threshold = a->histogram[a->compare_delay];
+    const int diff = cand - a->last_delay;
+    if (diff > a->allowed_offset) {
+        fraction = 1.f - 0.05f * (diff - a->allowed_offset);
+        fraction = fraction > 0.5f ? fraction : 0.5f;
+    } else if (diff < 0) {
+        fraction = 0.25f - 0.05f * diff;
+        fraction = fraction > 1.f ? 1.f : fraction;
+    }
+    threshold *= fraction;
+    threshold = threshold > 1.5f ? threshold : 1.5f;
+    return a->histogram[cand] >= threshold && a->candidate_hits > 10;
+}
+
+static int robust_validation(const OracleAecm *a, int cand, int instantaneous, int by_histogram) { /* :245-266 */
+    int robust = a->last_delay < 0 && (instantaneous || by_histogram);
+    robust |= instantaneous && by_histogram;
+    robust |= by_histogram && a->histogram[cand] > a->last_delay_histogram;
+    return robust;
+}
+
+/* WebRtc_ProcessBinarySpectrum, delay_estimator.cc:521-664.  AECM as shipped runs it with robust validation off and
+ * lookahead 0 (aecm_core.cc:218,225); the robust statistics are collected all the same (:628-633). */
 static int process_binary_spectrum(OracleAecm *a, uint32_t near_bits) {
     int32_t best = 32 << 9, worst = 0, depth;
     int cand = -1, valid, any_far = 0, d;
+    if (a->near_history_size > 1) { /* lookahead: delay the near-end binary spectrum, :536-543 */
+        memmove(&a->bin_near_hist[1], &a->bin_near_hist[0], (size_t)(a->near_history_size - 1) * sizeof(uint32_t));
+        a->bin_near_hist[0] = near_bits;
+        near_bits = a->bin_near_hist[a->lookahead];
+    }
     for (d = 0; d < OR_HIST; d++) { /* :545-564 */
         const uint32_t fw = far_word(a, d);
         const int fbits = __builtin_popcount(fw);
@@ -330,11 +383,90 @@ static int process_binary_spectrum(OracleAecm *a, uint32_t near_bits) {
     }
     a->last_delay_probability++; /* :608 */
     valid = depth > 1024 && (best < a->minimum_probability || best < a->last_delay_probability); /* :617-619 */
+    if (any_far && cand >= 0) update_robust_statistics(a, cand, depth, best); /* :628-633 */
+    if (a->robust_enabled && cand >= 0) /* :635-639 */
+        valid = robust_validation(a, cand, valid, histogram_based_validation(a, cand));
     if (any_far && valid) { /* :643-661 */
+        if (cand != a->last_delay) {
+            a->last_delay_histogram = a->histogram[cand] > 250.f ? 250.f : a->histogram[cand];
+            if (a->histogram[cand] < a->histogram[a->compare_delay]) a->histogram[a->compare_delay] = a->histogram[cand];
+        }
         a->last_delay = cand;
         if (best < a->last_delay_probability) a->last_delay_probability = best;
+        a->compare_delay = a->last_delay;
     }
     return a->last_delay;
+}
+
+/* WebRtc_InitBinaryDelayEstimator, delay_estimator.cc:483-504 (robust_validation_enabled, allowed_offset, lookahead
+ * and near_history_size belong to the estimator OBJECT and survive Init) */
+static void init_binary_delay_estimator(OracleAecm *a) {
+    int i;
+    if (a->near_history_size < 1) a->near_history_size = 1; /* a calloc'ed instance: WebRtc_CreateDelayEstimator(farend, 0) */
+    memset(a->bin_near_hist, 0, sizeof(a->bin_near_hist));
+    for (i = 0; i <= OR_HIST; i++) {
+        a->mean_bit_counts[i] = 20 << 9;
+        a->histogram[i] = 0.f;
+    }
+    a->minimum_probability = 32 << 9;
+    a->last_delay_probability = 32 << 9;
+    a->last_delay = -2;
+    a->last_candidate_delay = -2;
+    a->compare_delay = OR_HIST;
+    a->candidate_hits = 0;
+    a->last_delay_histogram = 0.f;
+}
+
+int32_t oracle_aecm_set_delay_estimator_options(OracleAecm *a, int robust, int allowed_offset, int max_lookahead, int lookahead) {
+    if (!a) return -1;
+    if (robust < 0 || robust > 1 || allowed_offset < 0 || max_lookahead > OR_MAX_LOOKAHEAD) return -1;
+    if (max_lookahead >= 0) { /* WebRtc_CreateDelayEstimator(farend, max_lookahead) + WebRtc_InitDelayEstimator */
+        a->near_history_size = max_lookahead + 1;
+        a->lookahead = max_lookahead;
+        a->robust_enabled = 0;
+        a->allowed_offset = 0;
+        memset(a->thr_near, 0, sizeof(a->thr_near));
+        a->thr_near_init = 0;
+        init_binary_delay_estimator(a);
+    }
+    if (a->near_history_size < 1) a->near_history_size = 1;
+    if (lookahead >= 0) { /* WebRtc_set_lookahead */
+        if (lookahead > a->near_history_size - 1) return -1;
+        a->lookahead = lookahead;
+    }
+    a->robust_enabled = robust;
+    a->allowed_offset = allowed_offset;
+    return 0;
+}
+
+int32_t oracle_aecm_soft_reset_delay_estimator(OracleAecm *a, int delay_shift) {
+    uint32_t shifted[OR_HIST];
+    const int abs_shift = delay_shift < 0 ? -delay_shift : delay_shift;
+    int i, old;
+    if (!a || abs_shift >= OR_HIST) return -1;
+    if (delay_shift != 0) { /* far end, delay_estimator.cc:336-367: shift the binary history, zero-fill the gap */
+        for (i = 0; i < OR_HIST; i++) {
+            const int src = i - delay_shift;
+            shifted[i] = (src >= 0 && src < OR_HIST) ? far_word(a, src) : 0u;
+        }
+        memcpy(a->bin_far, shifted, sizeof(shifted));
+        a->bin_far_head = 0;
+    }
+    if (a->near_history_size < 1) a->near_history_size = 1;
+    old = a->lookahead; /* near end, delay_estimator.cc:506-519 */
+    a->lookahead -= delay_shift;
+    if (a->lookahead < 0) a->lookahead = 0;
+    if (a->lookahead > a->near_history_size - 1) a->lookahead = a->near_history_size - 1;
+    return old - a->lookahead;
+}
+
+int32_t oracle_aecm_last_delay(const OracleAecm *a) { return a ? a->last_delay : -1; }
+
+float oracle_aecm_last_delay_quality(const OracleAecm *a) { /* delay_estimator.cc:671-688 */
+    float q;
+    if (a->robust_enabled) return a->histogram[a->compare_delay] / 3000.f;
+    q = (float)((32 << 9) - a->last_delay_probability) / (32 << 9);
+    return q < 0 ? 0 : q;
 }
 
 static int16_t log_energy_q8(uint32_t e, int q) { /* aecm_core.cc:612-628 */
@@ -823,10 +955,7 @@ static void init_core(OracleAecm *a, int fs) { /* aecm_core.cc:358-473 */
     memset(a->thr_near, 0, sizeof(a->thr_near));
     a->thr_far_init = 0;
     a->thr_near_init = 0;
-    for (i = 0; i < OR_HIST; i++) a->mean_bit_counts[i] = 20 << 9;
-    a->minimum_probability = 32 << 9;
-    a->last_delay_probability = 32 << 9;
-    a->last_delay = -2;
+    init_binary_delay_estimator(a);
     memset(a->far_hist, 0, sizeof(a->far_hist));
     memset(a->far_hist_q, 0, sizeof(a->far_hist_q));
     a->far_hist_pos = OR_HIST;

@@ -31,7 +31,8 @@ enum {
     OR_HIST = 100,     /* aecm_defines.h:26  MAX_DELAY  */
     OR_ELOG = 64,      /* aecm_defines.h:33  MAX_BUF_LEN */
     OR_FARRING = 4000, /* echo_control_mobile.cc:29,35  kBufSizeSamp */
-    OR_FRMRING = 144   /* aecm_core.cc:184  FRAME_LEN + PART_LEN */
+    OR_FRMRING = 144,  /* aecm_core.cc:184  FRAME_LEN + PART_LEN */
+    OR_MAX_LOOKAHEAD = 15 /* largest max_lookahead the checkers (and the product) accept; AECM itself uses 0 (aecm_core.cc:218) */
 };
 
 /* error codes, echo_control_mobile.h:22-30 */
@@ -108,8 +109,17 @@ typedef struct {
     int32_t thr_far_init, thr_near_init;
     uint32_t bin_far[OR_HIST];
     int32_t bin_far_head;
-    int32_t mean_bit_counts[OR_HIST];
+    int32_t mean_bit_counts[OR_HIST + 1]; /* + the dummy element used while last_delay == -2 (delay_estimator.cc:459-461) */
     int32_t minimum_probability, last_delay_probability, last_delay;
+    /* robust validation, lookahead, soft reset (delay_estimator.h:34-62).  AECM leaves all of it at the
+     * Create-time defaults (robust validation off, aecm_core.cc:225; max_lookahead 0, :218); the statistics are updated
+     * regardless, as in the reference (delay_estimator.cc:628-633). */
+    int32_t robust_enabled, allowed_offset;
+    int32_t near_history_size, lookahead;
+    uint32_t bin_near_hist[OR_MAX_LOOKAHEAD + 1];
+    float histogram[OR_HIST + 1];
+    float last_delay_histogram;
+    int32_t candidate_hits, last_candidate_delay, compare_delay;
 } OracleAecm;
 
 /* ---- the ten API entry points (echo_control_mobile.h:46-202), one instance per call ---- */
@@ -124,6 +134,19 @@ int32_t oracle_aecm_process(OracleAecm *a, const int16_t *near_noisy, const int1
 int32_t oracle_aecm_init_echo_path(OracleAecm *a, const void *echo_path, size_t size_bytes);
 int32_t oracle_aecm_get_echo_path(OracleAecm *a, void *echo_path, size_t size_bytes);
 size_t oracle_aecm_echo_path_size_bytes(void);
+/* SURVEY 8-f4, the delay estimator's knobs as AECM's estimator object would take them:
+ *   robust      WebRtc_enable_robust_validation (delay_estimator_wrapper.cc:421-434), 0/1
+ *   allowed_offset  WebRtc_set_allowed_offset (:401-409), >= 0
+ *   max_lookahead   >= 0: the estimator is re-created with this max_lookahead (WebRtc_CreateDelayEstimator, :289-336;
+ *                   lookahead starts at max_lookahead, delay_estimator.cc:433) and initialised; < 0: left as it is
+ *   lookahead       WebRtc_set_lookahead (:384-393) when >= 0
+ * Returns 0, or -1 where the reference call returns -1. */
+int32_t oracle_aecm_set_delay_estimator_options(OracleAecm *a, int robust, int allowed_offset, int max_lookahead, int lookahead);
+/* WebRtc_SoftResetDelayEstimatorFarend + WebRtc_SoftResetDelayEstimator (delay_estimator_wrapper.cc:227-231, 357-361;
+ * delay_estimator.cc:336-367, 506-519); returns what the latter returns (the lookahead shift actually applied) */
+int32_t oracle_aecm_soft_reset_delay_estimator(OracleAecm *a, int delay_shift);
+int32_t oracle_aecm_last_delay(const OracleAecm *a);             /* WebRtc_last_delay (:498-506) */
+float oracle_aecm_last_delay_quality(const OracleAecm *a);       /* WebRtc_last_delay_quality (:508-512) */
 size_t oracle_aecm_sizeof(void);
 
 /* ---- stage-level entry points for known-answer tests ---- */
@@ -155,6 +178,14 @@ typedef struct {
     int32_t skip_far_every;  /* >0: skip BufferFarend on calls where (call % skip)==skip-1 (underrun) */
     int32_t ms_per_call;     /* !=0: ms is [n_instances][n_calls], one msInSndCardBuf per call */
     int32_t extra_far_every; /* >0: BufferFarend is called TWICE (same frame) where (call % k)==k-1 (overrun) */
+    /* SURVEY 8-f4 (all zero = the reference's own wiring).  dly_options != 0: apply the four values below after
+     * Init/set_config through oracle_aecm_set_delay_estimator_options / the reference shim (max_lookahead and lookahead
+     * are passed as given, -1 = leave alone). */
+    int32_t dly_options;
+    int32_t dly_robust, dly_allowed_offset, dly_max_lookahead, dly_lookahead;
+    int32_t soft_reset_every; /* >0: soft-reset the delay estimator by soft_reset_shift before the calls with (call % k)==k-1,
+                                 the sign of the shift alternating from one reset to the next */
+    int32_t soft_reset_shift;
 } OracleRunConfig;
 /* planes are [n_instances][n_calls*samples_per_call] int16; ms is [n_instances] (or [n_instances][n_calls] with
  * ms_per_call) or NULL (=40);
@@ -163,6 +194,13 @@ typedef struct {
 int oracle_run_streams(const OracleRunConfig *cfg, int impl, const char *ref_lib_path,
                        const int16_t *far, const int16_t *near_noisy, const int16_t *near_clean,
                        const int16_t *ms, int16_t *out, int32_t *ret_or, double *seconds);
+
+/* the same, additionally recording the delay estimate after every call (WebRtc_last_delay) in delay_trace
+ * [n_instances][n_calls] when it is not NULL.  With impl 1 the delay-estimator options, soft resets and the trace need
+ * the reference SHIM library (oracle/_ref/libaecm_ref_shim.so) as ref_lib_path; -4 if its helpers are missing. */
+int oracle_run_streams_ex(const OracleRunConfig *cfg, int impl, const char *ref_lib_path,
+                          const int16_t *far, const int16_t *near_noisy, const int16_t *near_clean,
+                          const int16_t *ms, int16_t *out, int32_t *ret_or, int32_t *delay_trace, double *seconds);
 
 /* persistent pool (state survives across runs): warm up once, then time steady-state calls */
 typedef struct OraclePool OraclePool;

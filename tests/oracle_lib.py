@@ -16,13 +16,17 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 ORACLE_DIR = os.path.join(ROOT, "oracle")
 ORACLE_SO = os.path.join(ORACLE_DIR, "libaecm_oracle.so")
 REF_SO = os.path.join(ORACLE_DIR, "_ref", "libaecm_ref.so")
+REF_SHIM_SO = os.path.join(ORACLE_DIR, "_ref", "libaecm_ref_shim.so")  # the same objects + oracle/ref_shim.cc (SURVEY 8-f4 knobs)
 
 
 class RunConfig(C.Structure):
     _fields_ = [("n_instances", C.c_int32), ("fs", C.c_int32), ("samples_per_call", C.c_int32),
                 ("n_calls", C.c_int32), ("cng_mode", C.c_int32), ("echo_mode", C.c_int32),
                 ("use_clean", C.c_int32), ("n_threads", C.c_int32), ("skip_far_every", C.c_int32),
-                ("ms_per_call", C.c_int32), ("extra_far_every", C.c_int32)]
+                ("ms_per_call", C.c_int32), ("extra_far_every", C.c_int32),
+                ("dly_options", C.c_int32), ("dly_robust", C.c_int32), ("dly_allowed_offset", C.c_int32),
+                ("dly_max_lookahead", C.c_int32), ("dly_lookahead", C.c_int32), ("soft_reset_every", C.c_int32),
+                ("soft_reset_shift", C.c_int32)]
 
 
 _lib = None
@@ -41,6 +45,9 @@ def oracle():
         lib = C.CDLL(ORACLE_SO)
         lib.oracle_run_streams.restype = C.c_int
         lib.oracle_run_streams.argtypes = [C.POINTER(RunConfig), C.c_int, C.c_char_p] + [C.c_void_p] * 6 + [
+            C.POINTER(C.c_double)]
+        lib.oracle_run_streams_ex.restype = C.c_int
+        lib.oracle_run_streams_ex.argtypes = [C.POINTER(RunConfig), C.c_int, C.c_char_p] + [C.c_void_p] * 7 + [
             C.POINTER(C.c_double)]
         lib.oracle_aecm_create.restype = C.c_void_p
         for name in ("oracle_aecm_free", "oracle_aecm_init", "oracle_aecm_set_config", "oracle_aecm_buffer_farend",
@@ -82,19 +89,32 @@ def _ptr(a):
     return None if a is None else a.ctypes.data_as(C.c_void_p)
 
 
+def ref_shim_path():
+    return REF_SHIM_SO if os.path.exists(REF_SHIM_SO) else None
+
+
 def run_streams(far, near, *, fs=16000, samples_per_call=None, impl="oracle", clean=None, ms=None, cng_mode=1,
-                echo_mode=3, threads=None, skip_far_every=0, extra_far_every=0):
+                echo_mode=3, threads=None, skip_far_every=0, extra_far_every=0, dly=None, soft_reset=None,
+                delay_trace=False):
     """Run [n, T] int16 planes through the oracle ('oracle') or the reference library ('ref').
 
-    Returns (out[n, T] int16, ret_or[n] int32, seconds)."""
+    dly: None or dict(robust=, allowed_offset=, max_lookahead=, lookahead=) -- the delay estimator's knobs,
+    applied after Init/set_config; soft_reset: None or (every_k_calls, shift).  With impl='ref' these (and delay_trace)
+    go through the reference shim library.
+    Returns (out[n, T] int16, ret_or[n] int32, seconds), plus delay_trace[n, n_calls] int32 when delay_trace=True."""
     far = np.ascontiguousarray(far, dtype=np.int16)
     near = np.ascontiguousarray(near, dtype=np.int16)
     n, total = far.shape
     spc = samples_per_call or (160 if fs == 16000 else 80)
     assert total % spc == 0
     per_call = ms is not None and np.ndim(ms) == 2  # [n, n_calls]: one msInSndCardBuf per call
+    d = dly or {}
+    sr = soft_reset or (0, 0)
     cfg = RunConfig(n, fs, spc, total // spc, cng_mode, echo_mode, 0 if clean is None else 1,
-                    threads or min(os.cpu_count() or 1, max(n, 1)), skip_far_every, 1 if per_call else 0, extra_far_every)
+                    threads or min(os.cpu_count() or 1, max(n, 1)), skip_far_every, 1 if per_call else 0, extra_far_every,
+                    1 if dly else 0, d.get("robust", 0), d.get("allowed_offset", 0), d.get("max_lookahead", -1),
+                    d.get("lookahead", -1), sr[0], sr[1])
+    needs_shim = bool(dly) or sr[0] > 0 or delay_trace
     if clean is not None:
         clean = np.ascontiguousarray(clean, dtype=np.int16)
     if per_call:
@@ -107,14 +127,17 @@ def run_streams(far, near, *, fs=16000, samples_per_call=None, impl="oracle", cl
     secs = C.c_double(0)
     path = None
     if impl == "ref":
-        path = ref_path()
+        path = ref_shim_path() if needs_shim else ref_path()
         if path is None:
-            raise FileNotFoundError(REF_SO)
+            raise FileNotFoundError(REF_SHIM_SO if needs_shim else REF_SO)
         path = path.encode()
-    rc = oracle().oracle_run_streams(C.byref(cfg), 1 if impl == "ref" else 0, path, _ptr(far), _ptr(near), _ptr(clean),
-                                     _ptr(ms), _ptr(out), _ptr(ret), C.byref(secs))
+    trace = np.zeros((n, total // spc), dtype=np.int32) if delay_trace else None
+    rc = oracle().oracle_run_streams_ex(C.byref(cfg), 1 if impl == "ref" else 0, path, _ptr(far), _ptr(near), _ptr(clean),
+                                        _ptr(ms), _ptr(out), _ptr(ret), _ptr(trace), C.byref(secs))
     if rc != 0:
         raise RuntimeError(f"oracle_run_streams rc={rc}")
+    if delay_trace:
+        return out, ret, secs.value, trace
     return out, ret, secs.value
 
 
