@@ -104,6 +104,36 @@ int32_t AecmB200_BufferFarend(AecmB200Batch *batch, const int16_t *farend, size_
 int32_t AecmB200_Process(AecmB200Batch *batch, const int16_t *nearendNoisy, const int16_t *nearendClean, int16_t *out,
                          size_t nrOfSamples, const int16_t *msInSndCardBuf, int16_t msUniform, int32_t *status);
 
+/*
+ * SURVEY 8-f4 -- the delay estimator's optional machinery.  The reference's estimator object carries a robust-validation
+ * mode (a float histogram of candidate delays, delay_estimator.cc:96-266), a near-end lookahead (:536-543) and a soft
+ * reset (:336-367, 506-519); AECM wires it with robust validation off and max_lookahead 0 (aecm_core.cc:218, 225) and
+ * has no public call that reaches the estimator, so these three entry points have no counterpart among the ten
+ * WebRtcAecm_* symbols: they do to the estimator of every instance in the range what the cited setters of
+ * delay_estimator_wrapper.h do to one estimator handle.  Bit-exact against the reference driven through the same
+ * setters (float arithmetic included).  The first call of either of the first two switches the batch to the kernel
+ * instantiation that keeps the robust-validation statistics, which the reference keeps from Init on
+ * (delay_estimator.cc:628-633): to follow the reference exactly, set the options right after AecmB200_Init.  Options
+ * survive AecmB200_Init, as the properties of the reference's estimator object do; AecmB200_Reset clears them.
+ */
+typedef struct {
+    int32_t robustValidation; /* WebRtc_enable_robust_validation (delay_estimator_wrapper.cc:421-434): 0 or 1 */
+    int32_t allowedOffset;    /* WebRtc_set_allowed_offset (:401-409): >= 0 */
+    int32_t maxLookahead;     /* >= 0: the estimator is re-created with this max_lookahead (WebRtc_CreateDelayEstimator, :289-336; at
+                                 most 15; lookahead starts at maxLookahead, robust validation off, offset 0) and initialised
+                                 (WebRtc_InitDelayEstimator, :338-355) before the other fields are applied; -1: leave it */
+    int32_t lookahead;        /* WebRtc_set_lookahead (:384-393): 0 .. max_lookahead; -1: leave it */
+} AecmB200DelayEstimatorOptions;
+/* status: optional host array [count]: 0, AECM_UNINITIALIZED_ERROR, or -1 where WebRtc_set_lookahead refuses the value */
+int32_t AecmB200_SetDelayEstimatorOptions(AecmB200Batch *batch, int32_t first, int32_t count,
+                                          const AecmB200DelayEstimatorOptions *options, int32_t *status);
+/* WebRtc_SoftResetDelayEstimatorFarend + WebRtc_SoftResetDelayEstimator (:227-231, 357-361) with delayShift in (-100, 100);
+ * applied: optional host array [count] receiving what the latter returns (the lookahead shift actually applied). */
+int32_t AecmB200_SoftResetDelayEstimator(AecmB200Batch *batch, int32_t first, int32_t count, int32_t delayShift, int32_t *applied);
+/* WebRtc_last_delay (:498-506; -2 until the first valid estimate) and WebRtc_last_delay_quality (:508-512) per instance;
+ * either host array may be NULL. */
+int32_t AecmB200_GetDelayEstimate(AecmB200Batch *batch, int32_t first, int32_t count, int32_t *lastDelay, float *quality);
+
 /* Multi-GPU group: nInstances split into contiguous shards (ceil-split), one batch per entry of devices[] (NULL =
  * devices 0..nDevices-1), driven from the calling thread.  Instances are independent, so shards never exchange
  * data: a group call submits every shard's slice of the host planes asynchronously, then waits for all of them.

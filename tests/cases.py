@@ -204,3 +204,17 @@ def fft_adversarial_vectors(rng=None):
             inv.append(v)
     inv += [np.where(np.arange(130) % 2, 0, -32768)]
     return np.array(fwd, dtype=np.int16), np.array(inv, dtype=np.int16)
+
+
+# configurations of the delay estimator's optional machinery (oracle_lib.run_streams dly= / soft_reset=),
+# run on the delay-sweep inputs (per-instance echo delay 0..120 ms) where the estimate actually moves
+DLY_CONFIGS = [
+    dict(id="statistics_only", dly=dict(robust=0), soft_reset=None, instances=(0, 9)),
+    dict(id="robust", dly=dict(robust=1), soft_reset=None, instances=(1, 7, 14)),
+    dict(id="robust_offset3", dly=dict(robust=1, allowed_offset=3), soft_reset=None, instances=(2, 11)),
+    dict(id="lookahead5", dly=dict(robust=0, max_lookahead=5), soft_reset=None, instances=(3, 12)),
+    dict(id="robust_lookahead8_at3", dly=dict(robust=1, max_lookahead=8, lookahead=3), soft_reset=None, instances=(4, 13)),
+    dict(id="robust_lookahead4_softreset", dly=dict(robust=1, max_lookahead=4), soft_reset=(97, 3), instances=(5, 10)),
+    dict(id="softreset_only", dly=None, soft_reset=(50, 7), instances=(6, 15)),
+    dict(id="robust_softreset_back20", dly=dict(robust=1), soft_reset=(37, -20), instances=(8, 0)),
+]

@@ -15,6 +15,7 @@ namespace {
 struct Emu {
     alignas(16) AecmInstanceState st;
     alignas(16) WarpScratch sc;
+    alignas(16) AecmDelayExt ext;
     uint16_t far_hist[AECM_MAX_DELAY * AECM_HIST_ROW];
     int16_t far_ring[AECM_FAR_RING];
 };
@@ -28,18 +29,29 @@ size_t emu_state_bytes(void) { return sizeof(AecmInstanceState); }
 // One instance, n_calls API calls of `spc` samples.  ms: per-call msInSndCardBuf [n_calls].  far_ops: per call how
 // many times BufferFarend runs before Process (0 = underrun, 1 = normal, 2 = overrun).  Returns the OR of all return
 // codes; *state_out (optional) receives the final record.
+// dly (optional): {use, robust, allowed_offset, max_lookahead, lookahead, soft_reset_every, soft_reset_shift}: with
+// use != 0 the kExt instantiation runs, the options are applied after Init/set_config as AecmB200_SetDelayEstimatorOptions
+// does, and the delay estimator is soft-reset before the calls with (call % every) == every - 1, the sign of the shift
+// alternating (the schedule of oracle/aecm_runner.inc).  delay_trace (optional) [n_calls]: last_delay after every call.
 int emu_run_stream(int fs, int cng_mode, int echo_mode, const int16_t *far, const int16_t *near_noisy, const int16_t *near_clean,
                    int16_t *out, int n_calls, int spc, const int16_t *ms, const uint8_t *far_ops, void *state_out,
-                   long *barriers) {
+                   long *barriers, const int32_t *dly, int32_t *delay_trace) {
     Emu *e = new Emu();
     memset(e, 0, sizeof(*e));
     int acc = 0;
+    const bool ext = dly && dly[0];
     warp_emu::g_barriers = 0;
     warp_emu::run([&](int lane) {
         init_instance(&e->st, fs, lane);
+        init_delay_ext(&e->ext, lane);
         __syncwarp();
         if (lane == 0) apply_config(e->st.s, cng_mode, echo_mode);
         __syncwarp();
+        if (ext) {
+            const int r = set_delay_options(&e->st, &e->ext, dly[1], dly[2], dly[3], dly[4], lane);
+            if (lane == 0) acc |= r;
+            __syncwarp();
+        }
         Ctx c;
         c.st = &e->st;
         c.sc = &e->sc;
@@ -47,13 +59,22 @@ int emu_run_stream(int fs, int cng_mode, int echo_mode, const int16_t *far, cons
         c.far_hist_base = e->far_hist;
         c.far_ring_base = e->far_ring;
         c.inst = 0;
+        c.ext = &e->ext;
         c.lane = lane;
         for (int call = 0; call < n_calls; call++) {
             const size_t o = (size_t)call * (size_t)spc;
             int r = 0;
+            if (ext && dly[5] > 0 && (call % dly[5]) == dly[5] - 1) {
+                soft_reset_delay_estimator(&e->st, &e->ext, ((call / dly[5]) & 1) ? -dly[6] : dly[6], lane);
+                __syncwarp();
+            }
             for (int rep = 0; rep < (far_ops ? far_ops[call] : 1); rep++) r |= api_buffer_farend(c, far + o, spc);
-            r |= api_process(c, near_noisy + o, near_clean ? near_clean + o : nullptr, out + o, spc, ms ? ms[call] : 40);
-            if (lane == 0) acc |= r;
+            if (ext) r |= api_process<true>(c, near_noisy + o, near_clean ? near_clean + o : nullptr, out + o, spc, ms ? ms[call] : 40);
+            else r |= api_process<false>(c, near_noisy + o, near_clean ? near_clean + o : nullptr, out + o, spc, ms ? ms[call] : 40);
+            if (lane == 0) {
+                acc |= r;
+                if (delay_trace) delay_trace[call] = e->st.s.last_delay;
+            }
         }
     });
     if (state_out) memcpy(state_out, &e->st, sizeof(e->st));

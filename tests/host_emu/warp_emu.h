@@ -139,6 +139,12 @@ static inline int __popc(unsigned v) { return __builtin_popcount(v); }
 static inline unsigned __umulhi(unsigned a, unsigned b) { return (unsigned)(((uint64_t)a * b) >> 32); }
 static inline int __mulhi(int a, int b) { return (int)(((int64_t)a * b) >> 32); }
 static inline int __float2int_rz(float f) { return (int)f; }
+// single-precision operations with one rounding each (the emulation is built with -ffp-contract=off)
+static inline float __fadd_rn(float a, float b) { return a + b; }
+static inline float __fsub_rn(float a, float b) { return a - b; }
+static inline float __fmul_rn(float a, float b) { return a * b; }
+static inline float __fdiv_rn(float a, float b) { return a / b; }
+static inline float __int2float_rn(int v) { return (float)v; }
 static inline float __uint2float_rn(unsigned v) { return (float)v; }
 static inline unsigned __brev(unsigned v) {
     unsigned r = 0;

@@ -176,8 +176,11 @@ class OracleState(C.Structure):
         ("sup_diff_bd", C.c_int16), ("far_hist", C.c_uint16 * 6500), ("far_hist_pos", C.c_int32),
         ("far_hist_q", C.c_int32 * 100), ("thr_far", C.c_int32 * 65), ("thr_near", C.c_int32 * 65),
         ("thr_far_init", C.c_int32), ("thr_near_init", C.c_int32), ("bin_far", C.c_uint32 * 100),
-        ("bin_far_head", C.c_int32), ("mean_bit_counts", C.c_int32 * 100), ("minimum_probability", C.c_int32),
-        ("last_delay_probability", C.c_int32), ("last_delay", C.c_int32)]
+        ("bin_far_head", C.c_int32), ("mean_bit_counts", C.c_int32 * 101), ("minimum_probability", C.c_int32),
+        ("last_delay_probability", C.c_int32), ("last_delay", C.c_int32),
+        ("robust_enabled", C.c_int32), ("allowed_offset", C.c_int32), ("near_history_size", C.c_int32), ("lookahead", C.c_int32),
+        ("bin_near_hist", C.c_uint32 * 16), ("histogram", C.c_float * 101), ("last_delay_histogram", C.c_float),
+        ("candidate_hits", C.c_int32), ("last_candidate_delay", C.c_int32), ("compare_delay", C.c_int32)]
 
 
 class OracleInstance:
@@ -241,7 +244,7 @@ def compare_states(dev, orc: OracleState, use_clean=False):
     chk("thr_near", arr(dev.thr_near), arr(orc.thr_near)[12:44])
     dh, oh = S.bin_far_head, orc.bin_far_head
     chk("bin_far(by delay)", np.roll(arr(dev.bin_far, 100), -dh), np.roll(arr(orc.bin_far), -oh))
-    chk("mean_bit_counts", arr(dev.mean_bit_counts, 100), arr(orc.mean_bit_counts))
+    chk("mean_bit_counts", arr(dev.mean_bit_counts, 101), arr(orc.mean_bit_counts))  # incl. the dummy element [100]
     k = (S.log_head + np.arange(20)) & 31
     for f in ("near_log", "echo_adapt_log", "echo_stored_log"):
         chk(f, arr(getattr(dev, f))[k], arr(getattr(orc, f))[:20])

@@ -83,16 +83,23 @@ def test_built_kernel_keeps_its_launch_shape_and_hardware_paths():
         pytest.skip("cuobjdump not available")
     so = os.path.join(ROOT, "webrtc_aecm_b200", "libaecm_b200.so")
     res = subprocess.run(["cuobjdump", "-res-usage", so], capture_output=True, text=True).stdout
-    m = re.search(r"aecm_call_kernel\S*:\s*\n\s*REG:(\d+) STACK:(\d+) SHARED:\d+ LOCAL:(\d+)", res)
-    assert m, res[:400]
-    regs, stack, local = map(int, m.groups())
-    assert regs <= 72 and stack == 0 and local == 0, (regs, stack, local)
+    # two instantiations: <false> is the hot path (AECM as shipped), <true> additionally drives the delay estimator's
+    # optional machinery and may keep a few words on the stack
+    usage = {m.group(1): tuple(map(int, m.groups()[1:])) for m in
+             re.finditer(r"aecm_call_kernelILb([01])E\S*:\s*\n\s*REG:(\d+) STACK:(\d+) SHARED:\d+ LOCAL:(\d+)", res)}
+    assert set(usage) == {"0", "1"}, res[:600]
+    regs, stack, local = usage["0"]
+    assert regs <= 72 and stack == 0 and local == 0, usage
+    assert usage["1"][0] <= 72 and usage["1"][1] <= 64 and usage["1"][2] == 0, usage
     sass = subprocess.run(["cuobjdump", "-sass", so], capture_output=True, text=True).stdout
     assert "arch = sm_100a" in sass
-    call = sass[sass.index("aecm_call_kernel"):]
-    for mnemonic in ("UBLKCP.S.G", "UBLKCP.G.S", "SYNCS.PHASECHK", "MUFU.SQRT", "CREDUX"):
+    funcs = re.split(r"\n\s*Function : ", sass)
+    hot = [f for f in funcs if "aecm_call_kernelILb0E" in f.split("\n", 1)[0]]
+    assert len(hot) == 1
+    call = hot[0]
+    for mnemonic in ("UBLKCP.S.G", "UBLKCP.G.S", "SYNCS.PHASECHK", "MUFU.SQRT", "CREDUX", "BAR.SYNC"):
         assert mnemonic in call, mnemonic
-    assert not re.search(r"\b(LDL|STL)\b", call[:call.index("aecm_init_kernel")] if "aecm_init_kernel" in call else call)
+    assert not re.search(r"\b(LDL|STL)\b", call)
 
 
 def test_example_program_builds_against_the_public_headers(tmp_path):

@@ -12,7 +12,7 @@ import numpy as np
 import pytest
 
 import oracle_lib as ol
-from cases import CASE_BY_NAME, CASES, far_mask, make_inputs, run_kwargs
+from cases import CASE_BY_NAME, CASES, DLY_CONFIGS, far_mask, make_inputs, run_kwargs
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "..", "webrtc_aecm_b200", "csrc")
@@ -25,15 +25,18 @@ DEPS = [SRC, os.path.join(HERE, "host_emu", "warp_emu.h")] + [os.path.join(CSRC,
 @pytest.fixture(scope="module")
 def emu():
     if not os.path.exists(LIB) or any(os.path.getmtime(d) > os.path.getmtime(LIB) for d in DEPS):
-        subprocess.check_call(["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-I", os.path.join(HERE, "..", "include"), "-o", LIB, SRC])
+        subprocess.check_call(["g++", "-O2", "-ffp-contract=off", "-std=c++17", "-shared", "-fPIC", "-I", os.path.join(HERE, "..", "include"),
+                               "-o", LIB, SRC])
     lib = C.CDLL(LIB)
     lib.emu_state_bytes.restype = C.c_size_t
     lib.emu_run_stream.restype = C.c_int
     return lib
 
 
-def emu_run(lib, case, far, near, clean, ms, instance, want_state=False, misalign=False):
-    """One instance of a case through the emulated warp -> (out, or-of-return-codes, state bytes or None)."""
+def emu_run(lib, case, far, near, clean, ms, instance, want_state=False, misalign=False, dly=None, soft_reset=None,
+            delay_trace=None):
+    """One instance of a case through the emulated warp -> (out, or-of-return-codes, state bytes or None).
+    dly / soft_reset as in oracle_lib.run_streams (the kExt instantiation); delay_trace: int32 [calls] to fill."""
     spc = case["spc"]
     calls = far.shape[1] // spc
     if ms is None:
@@ -61,10 +64,17 @@ def emu_run(lib, case, far, near, clean, ms, instance, want_state=False, misalig
     out = plane(np.zeros_like(near[instance]))
     state = np.zeros(lib.emu_state_bytes(), dtype=np.uint8) if want_state else None
     nbar = C.c_long(0)
+    dly_arr = None
+    if dly is not None or soft_reset is not None:
+        d, sr = dly or {}, soft_reset or (0, 0)
+        dly_arr = np.array([1, d.get("robust", 0), d.get("allowed_offset", 0), d.get("max_lookahead", -1), d.get("lookahead", -1),
+                            sr[0], sr[1]], dtype=np.int32)
     acc = lib.emu_run_stream(case["fs"], case["cng"], case["echo_mode"], f.ctypes.data_as(C.c_void_p), x.ctypes.data_as(C.c_void_p),
                              None if cl is None else cl.ctypes.data_as(C.c_void_p), out.ctypes.data_as(C.c_void_p), calls, spc,
                              ms_calls.ctypes.data_as(C.c_void_p), ops.ctypes.data_as(C.c_void_p),
-                             None if state is None else state.ctypes.data_as(C.c_void_p), C.byref(nbar))
+                             None if state is None else state.ctypes.data_as(C.c_void_p), C.byref(nbar),
+                             None if dly_arr is None else dly_arr.ctypes.data_as(C.c_void_p),
+                             None if delay_trace is None else delay_trace.ctypes.data_as(C.c_void_p))
     return out, acc, state
 
 
@@ -114,3 +124,24 @@ def test_final_record_equals_oracle_state_field_by_field(emu):
     dev = api.InstanceState.from_buffer_copy(state.tobytes())
     assert ol.compare_states(dev, o.state()) == []
     o.close()
+
+
+@pytest.mark.parametrize("cfg", DLY_CONFIGS, ids=[c["id"] for c in DLY_CONFIGS])
+def test_delay_estimator_options_on_emulated_warp(emu, cfg):
+    """SURVEY 8-f4 on the device code (kExt instantiation: robust validation with its float histogram, near-end lookahead,
+    soft resets), run on the emulated warp: output AND the delay estimate after every call equal the oracle's, which
+    tests/test_oracle.py pins to the reference driven through its own setters."""
+    case = CASE_BY_NAME["c5_delay_sweep_0_120ms"]
+    far, near, clean, ms = make_inputs(case)
+    spc = case["spc"]
+    calls = far.shape[1] // spc
+    want, ret, _, trace = ol.run_streams(far, near, impl="oracle", ms=ms, dly=cfg["dly"], soft_reset=cfg["soft_reset"],
+                                         delay_trace=True, **run_kwargs(case))
+    for instance in cfg["instances"]:
+        got_trace = np.zeros(calls, dtype=np.int32)
+        out, acc, _ = emu_run(emu, case, far, near, None, ms, instance, dly=cfg["dly"], soft_reset=cfg["soft_reset"],
+                              delay_trace=got_trace)
+        bad = np.nonzero(out != want[instance])[0]
+        assert bad.size == 0, f"instance {instance}: first differing sample {bad[0]} (call {bad[0] // spc})"
+        np.testing.assert_array_equal(got_trace, trace[instance])
+        assert acc == 0 and ret[instance] == 0

@@ -552,3 +552,105 @@ def test_group_sharding_over_devices_matches_oracle():
     assert L.AecmB200_GroupWaitStream(g, (calls - 1) % 2) == 0
     np.testing.assert_array_equal(ho.transpose(1, 0, 2).reshape(n, calls * spc), want)
     L.AecmB200_GroupFree(g)
+
+
+DLY_GOLD = json.load(open(os.path.join(GOLD, "dly_streams.json")))["cases"]
+
+
+@pytest.mark.parametrize("cfg", __import__("cases").DLY_CONFIGS, ids=[c["id"] for c in __import__("cases").DLY_CONFIGS])
+def test_delay_estimator_options_match_reference(cfg):
+    """SURVEY 8-f4 through the C ABI (AecmB200_SetDelayEstimatorOptions / _SoftResetDelayEstimator / _GetDelayEstimate): robust
+    validation with its float histogram, near-end lookahead and soft resets on the delay-sweep inputs.  Output AND the
+    delay estimate after every call must equal the oracle's, the checksums of the reference driven through its own
+    setters (tests/golden/dly_streams.json), and that reference itself when oracle/_ref/libaecm_ref_shim.so travelled."""
+    from webrtc_aecm_b200 import AecmBatch
+
+    case = CASE_BY_NAME["c5_delay_sweep_0_120ms"]
+    far, near, clean, ms = make_inputs(case)
+    n, total = far.shape
+    spc = case["spc"]
+    calls = total // spc
+    want, ret, _, wtrace = ol.run_streams(far, near, impl="oracle", ms=ms, dly=cfg["dly"], soft_reset=cfg["soft_reset"], delay_trace=True,
+                                          **run_kwargs(case))
+    b = AecmBatch(n, 0)
+    assert b.init(case["fs"]) == 0
+    rc, st = b.set_config(case["cng"], case["echo_mode"])
+    assert rc == 0 and not st.any()
+    if cfg["dly"] is not None:
+        rc, st = b.set_delay_estimator_options(**cfg["dly"])
+        assert rc == 0 and not st.any()
+    every, shift = cfg["soft_reset"] or (0, 0)
+    out = np.zeros_like(near)
+    trace = np.zeros((n, calls), dtype=np.int32)
+    for c in range(calls):  # one launch per call: the delay estimate is read back after each
+        if every and c % every == every - 1:
+            rc, applied = b.soft_reset_delay_estimator(-shift if (c // every) & 1 else shift)
+            assert rc == 0
+        sl = slice(c * spc, (c + 1) * spc)
+        rc, o, status = b.process_stream(np.ascontiguousarray(far[:, sl]), np.ascontiguousarray(near[:, sl]), samples_per_call=spc,
+                                         ms=ms, ms_uniform=40)
+        assert rc == 0 and not status.any()
+        out[:, sl] = o
+        rc, d, q = b.delay_estimate()
+        assert rc == 0
+        trace[:, c] = d
+    bad = np.nonzero((out != want).any(axis=1))[0]
+    assert bad.size == 0, f"instances {bad[:8]} differ, first sample {np.argmax(out[bad[0]] != want[bad[0]])}"
+    np.testing.assert_array_equal(trace, wtrace)
+    gold = DLY_GOLD[cfg["id"]]
+    assert stream_checksum(out) == gold["sha256"] and stream_checksum(trace) == gold["delay_trace_sha256"]
+    assert np.isfinite(q).all() and (q >= 0).all() and (q <= 1).all()
+    if ol.ref_shim_path():
+        rout, _, _, rtrace = ol.run_streams(far, near, impl="ref", ms=ms, dly=cfg["dly"], soft_reset=cfg["soft_reset"], delay_trace=True,
+                                            **run_kwargs(case))
+        np.testing.assert_array_equal(out, rout)
+        np.testing.assert_array_equal(trace, rtrace)
+    b.close()
+
+
+def test_delay_estimator_options_fused_calls_error_codes_and_init_semantics():
+    """(a) Robust validation with many calls fused per launch equals call by call; (b) argument checking follows the reference's
+    setters; (c) the options belong to the estimator object: they survive AecmB200_Init, AecmB200_Reset clears them; (d) soft
+    reset returns the lookahead shift actually applied (delay_estimator.cc:506-519)."""
+    import ctypes as C
+
+    from webrtc_aecm_b200 import AecmBatch, api
+
+    case = CASE_BY_NAME["c5_delay_sweep_0_120ms"]
+    far, near, clean, ms = make_inputs(case)
+    dly = dict(robust=1, allowed_offset=2, max_lookahead=6, lookahead=2)
+    want, _, _ = ol.run_streams(far, near, impl="oracle", ms=ms, dly=dly, **run_kwargs(case))
+    n = far.shape[0]
+    b = AecmBatch(n, 0)
+    rc, st = b.set_delay_estimator_options(robust=1)
+    assert rc == 0 and (st == api.AECM_UNINITIALIZED_ERROR).all()
+    assert b.init(16000) == 0
+    rc, st = b.set_delay_estimator_options(**dly)
+    assert rc == 0 and not st.any()
+    rc, out, status = b.process_stream(far, near, samples_per_call=160, ms=ms)  # 600 calls in one launch
+    assert rc == 0 and not status.any()
+    np.testing.assert_array_equal(out, want)
+    # (c) Init keeps the options (lookahead as last set), so a second run from Init reproduces the same output ...
+    assert b.init(16000) == 0
+    rc, out2, status = b.process_stream(far, near, samples_per_call=160, ms=ms)
+    np.testing.assert_array_equal(out2, want)
+    # (b)
+    L = api.lib()
+    for bad in (api.DelayEstimatorOptions(2, 0, -1, -1), api.DelayEstimatorOptions(0, -1, -1, -1), api.DelayEstimatorOptions(0, 0, 16, -1),
+                api.DelayEstimatorOptions(0, 0, 3, 4)):
+        assert L.AecmB200_SetDelayEstimatorOptions(b._h, 0, n, C.byref(bad), None) == api.AECM_BAD_PARAMETER_ERROR
+    assert L.AecmB200_SetDelayEstimatorOptions(b._h, 0, n, None, None) == api.AECM_NULL_POINTER_ERROR
+    assert L.AecmB200_SoftResetDelayEstimator(b._h, 0, n, 100, None) == api.AECM_BAD_PARAMETER_ERROR
+    rc, st = b.set_delay_estimator_options(robust=1, allowed_offset=2, lookahead=7)  # beyond max_lookahead 6: WebRtc_set_lookahead -> -1
+    assert rc == 0 and (st == -1).all()
+    # (d) lookahead 2, near history 7: +1 -> 1 (applied 1); +5 -> 0 (applied 1); -9 -> 6 (applied -6)
+    for shift, applied in ((1, 1), (5, 1), (-9, -6)):
+        rc, got = b.soft_reset_delay_estimator(shift)
+        assert rc == 0 and (got == applied).all(), (shift, got)
+    # ... and Reset returns to AECM's own wiring: the default output
+    b.reset()
+    assert b.init(16000) == 0
+    base, _, _ = ol.run_streams(far, near, impl="oracle", ms=ms, **run_kwargs(case))
+    rc, out3, status = b.process_stream(far, near, samples_per_call=160, ms=ms)
+    np.testing.assert_array_equal(out3, base)
+    b.close()

@@ -9,7 +9,7 @@ import numpy as np
 import pytest
 
 import oracle_lib as ol
-from cases import CASES, make_inputs, run_kwargs
+from cases import CASE_BY_NAME, CASES, DLY_CONFIGS, make_inputs, run_kwargs
 from webrtc_aecm_b200.shard import stream_checksum
 
 GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
@@ -226,3 +226,49 @@ def test_live_config_and_echo_path_changes_oracle_equals_reference():
     np.testing.assert_array_equal(a, b)
     ref.WebRtcAecm_Free(r)
     o.close()
+
+
+DLY_GOLD = json.load(open(os.path.join(GOLD, "dly_streams.json")))["cases"]
+
+
+@pytest.mark.parametrize("cfg", DLY_CONFIGS, ids=[c["id"] for c in DLY_CONFIGS])
+def test_delay_estimator_options_oracle_equals_reference(cfg):
+    """robust validation (float histogram), lookahead and soft resets.  The oracle must reproduce the checksums
+    of the reference driven through its own setters (tests/golden/dly_streams.json, written by tools/make_golden.py via
+    oracle/ref_shim.cc) -- output and the delay estimate after every call -- and, where the shim library is present, the
+    arrays themselves."""
+    case = CASE_BY_NAME["c5_delay_sweep_0_120ms"]
+    far, near, clean, ms = make_inputs(case)
+    out, ret, _, trace = ol.run_streams(far, near, impl="oracle", ms=ms, dly=cfg["dly"], soft_reset=cfg["soft_reset"], delay_trace=True,
+                                        **run_kwargs(case))
+    gold = DLY_GOLD[cfg["id"]]
+    assert stream_checksum(out) == gold["sha256"] and stream_checksum(trace) == gold["delay_trace_sha256"]
+    assert [int(r) for r in ret] == gold["ret_or"]
+    if ol.ref_shim_path():
+        rout, rret, _, rtrace = ol.run_streams(far, near, impl="ref", ms=ms, dly=cfg["dly"], soft_reset=cfg["soft_reset"],
+                                               delay_trace=True, **run_kwargs(case))
+        np.testing.assert_array_equal(out, rout)
+        np.testing.assert_array_equal(trace, rtrace)
+        np.testing.assert_array_equal(ret, rret)
+
+
+def test_delay_estimator_options_change_the_estimate():
+    """The configurations are not vacuous: robust validation, lookahead and soft resets each move the output away from the
+    default wiring on these inputs, and the setters refuse what the reference's refuse."""
+    base = json.load(open(os.path.join(GOLD, "streams.json")))["cases"]["c5_delay_sweep_0_120ms"]["sha256"]
+    shas = {k: v["sha256"] for k, v in DLY_GOLD.items()}
+    assert shas["statistics_only"] == base  # collecting the statistics alone changes nothing (aecm_core.cc:225)
+    assert len(set(shas.values())) == len(shas) and all(v != base for k, v in shas.items() if k != "statistics_only")
+    lib = ol.oracle()
+    a = lib.oracle_aecm_create()
+    lib.oracle_aecm_init(C.c_void_p(a), 16000)
+    f = lib.oracle_aecm_set_delay_estimator_options
+    f.argtypes = [C.c_void_p] + [C.c_int] * 4
+    assert f(a, 2, 0, -1, -1) == -1 and f(a, 1, -1, -1, -1) == -1  # delay_estimator_wrapper.cc:404, 427
+    assert f(a, 0, 0, -1, 1) == -1  # lookahead beyond max_lookahead (0): :388-391
+    assert f(a, 1, 2, 6, 4) == 0 and f(a, 1, 2, -1, 7) == -1
+    lib.oracle_aecm_soft_reset_delay_estimator.argtypes = [C.c_void_p, C.c_int]
+    assert lib.oracle_aecm_soft_reset_delay_estimator(a, 3) == 3  # lookahead 4 -> 1
+    assert lib.oracle_aecm_soft_reset_delay_estimator(a, 3) == 1  # 1 -> 0 (clamped)
+    assert lib.oracle_aecm_soft_reset_delay_estimator(a, -9) == -6  # 0 -> 6 (clamped to max_lookahead)
+    lib.oracle_aecm_free(C.c_void_p(a))

@@ -5,6 +5,8 @@ Run in the build container (needs /root/reference to have been compiled by oracl
     python tools/make_golden.py
 Writes
     tests/golden/streams.json   per case: sha256 of the reference's int16 output + OR of its return codes
+    tests/golden/dly_streams.json     SURVEY 8-f4: output / delay-trace checksums of the reference with robust validation, lookahead
+                                      and soft resets switched on through oracle/ref_shim.cc
     tests/golden/fft_adversarial.npz  a larger adversarial FFT/IFFT family with the reference's answers
     tests/golden/vectors.npz    full reference outputs for two small cases, and stage-level known-answer
                                 vectors produced by the reference's own C symbols (forward/inverse real FFT
@@ -24,7 +26,7 @@ sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 import oracle_lib as ol  # noqa: E402
-from cases import CASES, fft_adversarial_vectors, make_inputs, run_kwargs  # noqa: E402
+from cases import CASE_BY_NAME, CASES, DLY_CONFIGS, fft_adversarial_vectors, make_inputs, run_kwargs  # noqa: E402
 from webrtc_aecm_b200.shard import stream_checksum  # noqa: E402
 
 FULL_VECTOR_CASES = ("16k_80_sample_calls", "16k_full_scale_alternating")
@@ -101,6 +103,19 @@ def main():
         if case["name"] in FULL_VECTOR_CASES:
             vectors["out__" + case["name"]] = out
         print(case["name"], streams[case["name"]]["sha256"][:16], sorted(set(ret.tolist())))
+    # the delay estimator's optional machinery, driven on the reference through oracle/ref_shim.cc
+    dly = {}
+    case = CASE_BY_NAME["c5_delay_sweep_0_120ms"]
+    far, near, clean, ms = make_inputs(case)
+    for cfg in DLY_CONFIGS:
+        out, ret, _, trace = ol.run_streams(far, near, impl="ref", ms=ms, dly=cfg["dly"], soft_reset=cfg["soft_reset"], delay_trace=True,
+                                            **run_kwargs(case))
+        dly[cfg["id"]] = {"sha256": stream_checksum(out), "delay_trace_sha256": stream_checksum(trace), "ret_or": [int(r) for r in ret],
+                          "distinct_delays": int(len(np.unique(trace)))}
+        print("dly", cfg["id"], dly[cfg["id"]]["sha256"][:16], dly[cfg["id"]]["distinct_delays"])
+    with open(os.path.join(ROOT, "tests", "golden", "dly_streams.json"), "w") as f:
+        json.dump({"generator": "tools/make_golden.py", "source": "oracle/_ref/libaecm_ref_shim.so (unmodified reference + oracle/ref_shim.cc)",
+                   "inputs": "tests/cases.py c5_delay_sweep_0_120ms, configurations DLY_CONFIGS", "cases": dly}, f, indent=1, sort_keys=True)
     vectors.update(stage_vectors(C.CDLL(ol.ref_path())))
     gdir = os.path.join(ROOT, "tests", "golden")
     os.makedirs(gdir, exist_ok=True)

@@ -38,6 +38,11 @@ class StreamArgs(C.Structure):
                 ("farendMask", C.c_void_p), ("status", C.c_void_p), ("instanceIndex", C.c_void_p)]
 
 
+class DelayEstimatorOptions(C.Structure):
+    """``AecmB200DelayEstimatorOptions`` of aecm_b200.h."""
+    _fields_ = [("robustValidation", C.c_int32), ("allowedOffset", C.c_int32), ("maxLookahead", C.c_int32), ("lookahead", C.c_int32)]
+
+
 class Scalars(C.Structure):
     """``AecmScalars`` of csrc/aecm_state.h (introspection only)."""
     _fields_ = [(n, C.c_int32) for n in (
@@ -103,6 +108,9 @@ def lib():
             "AecmB200_AdoptCudaStream": (i32, [vp, vp]),
             "AecmB200_HostAlloc": (vp, [C.c_size_t]), "AecmB200_HostFree": (None, [vp]),
             "AecmB200_SelfTestSqrtFloor": (C.c_int64, [C.c_uint32, C.c_uint32]), "AecmB200_NumStreamSlots": (i32, []),
+            "AecmB200_SetDelayEstimatorOptions": (i32, [vp, i32, i32, C.POINTER(DelayEstimatorOptions), vp]),
+            "AecmB200_SoftResetDelayEstimator": (i32, [vp, i32, i32, i32, vp]),
+            "AecmB200_GetDelayEstimate": (i32, [vp, i32, i32, vp, vp]),
             "AecmB200_SelfTestFftForward": (i32, [vp, vp, i32, i32]), "AecmB200_SelfTestFftInverse": (i32, [vp, vp, vp, i32]),
             "AecmB200_ScalarApiStats": (None, [vp, C.POINTER(i64), C.POINTER(i64)]),
             "AecmB200_StateBytes": (C.c_size_t, []), "AecmB200_ReadState": (i32, [vp, i32, vp, C.c_size_t]),
@@ -238,6 +246,25 @@ class AecmBatch:
         rc = self._lib.AecmB200_Process(self._h, _host_ptr(near), _host_ptr(clean), _host_ptr(out), near.shape[1],
                                         _host_ptr(ms), int(ms_uniform), _host_ptr(status))
         return rc, out, status
+
+    def set_delay_estimator_options(self, robust=0, allowed_offset=0, max_lookahead=-1, lookahead=-1, first=0, count=None):
+        count = self.n - first if count is None else count
+        status = np.zeros(count, dtype=np.int32)
+        o = DelayEstimatorOptions(robust, allowed_offset, max_lookahead, lookahead)
+        rc = self._lib.AecmB200_SetDelayEstimatorOptions(self._h, first, count, C.byref(o), _host_ptr(status))
+        return rc, status
+
+    def soft_reset_delay_estimator(self, delay_shift, first=0, count=None):
+        count = self.n - first if count is None else count
+        applied = np.zeros(count, dtype=np.int32)
+        rc = self._lib.AecmB200_SoftResetDelayEstimator(self._h, first, count, int(delay_shift), _host_ptr(applied))
+        return rc, applied
+
+    def delay_estimate(self, first=0, count=None):
+        count = self.n - first if count is None else count
+        delay, quality = np.zeros(count, dtype=np.int32), np.zeros(count, dtype=np.float32)
+        rc = self._lib.AecmB200_GetDelayEstimate(self._h, first, count, _host_ptr(delay), _host_ptr(quality))
+        return rc, delay, quality
 
     def synchronize(self):
         self._check(self._lib.AecmB200_Synchronize(self._h), "Synchronize")

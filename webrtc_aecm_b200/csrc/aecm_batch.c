@@ -46,6 +46,8 @@ struct AecmB200Batch {
     int trace;
     int32_t *d_status;      /* scratch for the control calls (set_config, echo path) */
     int16_t *d_path;
+    int ext_active;         /* the delay estimator's optional machinery is in use: launches run the kExt kernel */
+    float *d_quality;       /* scratch for AecmB200_GetDelayEstimate */
     uint64_t *index_seen;   /* bitmap over the instances, for the duplicate check of instanceIndex (allocated on first use) */
     char err[256];
 };
@@ -102,6 +104,8 @@ AecmB200Batch *AecmB200_Create(int32_t n, int32_t device) {
     if (cudaMalloc((void **)&b->planes.state, (size_t)n * sizeof(AecmInstanceState)) != cudaSuccess ||
         cudaMalloc((void **)&b->planes.far_hist, (size_t)n * AECM_MAX_DELAY * AECM_HIST_ROW * sizeof(uint16_t)) != cudaSuccess ||
         cudaMalloc((void **)&b->planes.far_ring, (size_t)n * AECM_FAR_RING * sizeof(int16_t)) != cudaSuccess ||
+        cudaMalloc((void **)&b->planes.dly_ext, (size_t)n * sizeof(AecmDelayExt)) != cudaSuccess ||
+        cudaMalloc((void **)&b->d_quality, (size_t)n * sizeof(float)) != cudaSuccess ||
         cudaMalloc((void **)&b->d_status, (size_t)n * sizeof(int32_t)) != cudaSuccess ||
         cudaMalloc((void **)&b->d_path, AECM_BINS * sizeof(int16_t)) != cudaSuccess ||
         cudaStreamCreateWithFlags(&b->stream, cudaStreamNonBlocking) != cudaSuccess) {
@@ -134,6 +138,7 @@ AecmB200Batch *AecmB200_Create(int32_t n, int32_t device) {
     b->owns_stream = 1;
     /* calloc semantics of the reference's Create: an un-Init'ed instance reports AECM_UNINITIALIZED_ERROR */
     if (cudaMemsetAsync(b->planes.state, 0, (size_t)n * sizeof(AecmInstanceState), b->stream) != cudaSuccess ||
+        cudaMemsetAsync(b->planes.dly_ext, 0, (size_t)n * sizeof(AecmDelayExt), b->stream) != cudaSuccess ||
         cudaStreamSynchronize(b->stream) != cudaSuccess) {
         AecmB200_Free(b);
         return NULL;
@@ -149,6 +154,8 @@ void AecmB200_Free(AecmB200Batch *b) {
     cudaFree(b->planes.state);
     cudaFree(b->planes.far_hist);
     cudaFree(b->planes.far_ring);
+    cudaFree(b->planes.dly_ext);
+    cudaFree(b->d_quality);
     for (int i = 0; i < AECM_SLOTS; i++) {
         Slot *sl = &b->slot[i];
         if (sl->copy) cudaStreamSynchronize(sl->copy);
@@ -248,6 +255,7 @@ int32_t AecmB200_Reset(AecmB200Batch *b, int32_t first, int32_t count) {
     ENTER_DEVICE(b);
     if (use_main_stream(b)) return AECM_UNSPECIFIED_ERROR;
     CU(b, cudaMemsetAsync(b->planes.state + first, 0, (size_t)count * sizeof(AecmInstanceState), b->stream));
+    CU(b, cudaMemsetAsync(b->planes.dly_ext + first, 0, (size_t)count * sizeof(AecmDelayExt), b->stream));
     CU(b, cudaStreamSynchronize(b->stream));
     return 0;
 }
@@ -312,6 +320,45 @@ int32_t AecmB200_GetEchoPath(AecmB200Batch *b, int32_t instance, void *path, siz
     return 0;
 }
 
+/* ---- the delay estimator's optional machinery (robust validation, lookahead, soft reset) ---- */
+int32_t AecmB200_SetDelayEstimatorOptions(AecmB200Batch *b, int32_t first, int32_t count, const AecmB200DelayEstimatorOptions *o,
+                                          int32_t *status) {
+    if (!b) return -1;
+    if (!o) return AECM_NULL_POINTER_ERROR;
+    if (!range_ok(b, first, count)) return AECM_BAD_PARAMETER_ERROR;
+    /* what the reference's setters reject for any estimator (delay_estimator_wrapper.cc:401-434) or its Create cannot hold */
+    if ((o->robustValidation != 0 && o->robustValidation != 1) || o->allowedOffset < 0 || o->maxLookahead > AECM_MAX_LOOKAHEAD ||
+        (o->maxLookahead >= 0 && o->lookahead > o->maxLookahead))
+        return AECM_BAD_PARAMETER_ERROR;
+    ENTER_DEVICE(b);
+    if (use_main_stream(b)) return AECM_UNSPECIFIED_ERROR;
+    b->ext_active = 1;
+    CU(b, (cudaError_t)aecm_cuda_launch_dly_options(&b->planes, first, count, o->robustValidation, o->allowedOffset, o->maxLookahead,
+                                                    o->lookahead, b->d_status, b->stream));
+    return copy_status_out(b, status, count);
+}
+
+int32_t AecmB200_SoftResetDelayEstimator(AecmB200Batch *b, int32_t first, int32_t count, int32_t delayShift, int32_t *applied) {
+    if (!b) return -1;
+    if (!range_ok(b, first, count)) return AECM_BAD_PARAMETER_ERROR;
+    if (delayShift <= -AECM_MAX_DELAY || delayShift >= AECM_MAX_DELAY) return AECM_BAD_PARAMETER_ERROR; /* delay_estimator.cc:346-347 */
+    ENTER_DEVICE(b);
+    if (use_main_stream(b)) return AECM_UNSPECIFIED_ERROR;
+    b->ext_active = 1;
+    CU(b, (cudaError_t)aecm_cuda_launch_dly_soft_reset(&b->planes, first, count, delayShift, b->d_status, b->stream));
+    return copy_status_out(b, applied, count);
+}
+
+int32_t AecmB200_GetDelayEstimate(AecmB200Batch *b, int32_t first, int32_t count, int32_t *lastDelay, float *quality) {
+    if (!b) return -1;
+    if (!range_ok(b, first, count)) return AECM_BAD_PARAMETER_ERROR;
+    ENTER_DEVICE(b);
+    if (use_main_stream(b)) return AECM_UNSPECIFIED_ERROR;
+    CU(b, (cudaError_t)aecm_cuda_launch_dly_query(&b->planes, first, count, b->d_status, b->d_quality, b->stream));
+    if (quality) CU(b, cudaMemcpyAsync(quality, b->d_quality, (size_t)count * sizeof(float), cudaMemcpyDeviceToHost, b->stream));
+    return copy_status_out(b, lastDelay, count);
+}
+
 static int32_t validate_stream_args(const AecmB200Batch *b, const AecmB200StreamArgs *a) {
     if (!a) return AECM_NULL_POINTER_ERROR;
     if (!a->farend && !a->nearendNoisy) return AECM_NULL_POINTER_ERROR;
@@ -352,6 +399,7 @@ int32_t AecmB200_ProcessStreamDevice(AecmB200Batch *b, const AecmB200StreamArgs 
     ENTER_DEVICE(b);
     if (use_main_stream(b)) return AECM_UNSPECIFIED_ERROR;
     fill_call_args(&k, a);
+    k.ext = b->ext_active;
     CU(b, (cudaError_t)aecm_cuda_launch_call(&b->planes, &k, b->stream));
     return 0;
 }
@@ -500,6 +548,7 @@ static int32_t enqueue_stream(AecmB200Batch *b, const AecmB200StreamArgs *h, Slo
     k.samples_per_call = h->nrOfSamples;
     k.n_calls = h->nCalls;
     k.ms_uniform = h->msUniform;
+    k.ext = b->ext_active;
     if (b->trace) CU(b, cudaEventRecord(sl->t[1], sl->copy));
     /* the state recurrence: this kernel must follow the previous submission's kernel (on the other slot's stream) */
     if (b->last_kernel) CU(b, cudaStreamWaitEvent(sl->copy, b->last_kernel, 0));

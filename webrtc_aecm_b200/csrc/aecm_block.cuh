@@ -85,11 +85,32 @@ __device__ __forceinline__ uint32_t binary_spectrum(const uint16_t *spec, int32_
     return __ballot_sync(kFull, s15 > t);
 }
 
-// WebRtc_ProcessBinarySpectrum (delay_estimator.cc:521-664) with robust validation off, lookahead 0.  The three
-// scalars of the estimator are passed in registers (warp-uniform) and updated in place.
-__device__ __forceinline__ void process_binary_spectrum(AecmInstanceState *st, uint32_t near_bits, int head, int lane,
-                                                        int &minimum_probability, int &last_delay_probability,
-                                                        int &last_delay) {
+// WebRtc_ProcessBinarySpectrum (delay_estimator.cc:521-664).  The three scalars of the estimator are passed in registers
+// (warp-uniform) and updated in place.  kExt = false is AECM as shipped: robust validation off, lookahead 0
+// (aecm_core.cc:218,225), the float statistics that cannot reach the output are not kept.  kExt = true adds
+// the near-end lookahead (:536-543), UpdateRobustValidationStatistics (:96-154), HistogramBasedValidation (:178-225) and
+// RobustValidation (:245-266) on the instance's AecmDelayExt record in HBM.  The float arithmetic is written with the
+// round-to-nearest intrinsics, one rounding per operation in the reference's order, so that no multiply-add is fused:
+// the reference library is built for baseline x86-64 (SSE2, no FMA), where every float operation rounds on its own.
+template <bool kExt>
+__device__ __forceinline__ void process_binary_spectrum(const Ctx &c, uint32_t near_bits, int head, int &minimum_probability,
+                                                        int &last_delay_probability, int &last_delay) {
+    AecmInstanceState *st = c.st;
+    AecmDelayExt *e = c.ext;
+    const int lane = c.lane;
+    if (kExt) {
+        const int near_size = max(e->near_size, 1);
+        if (near_size > 1) {  // delay the near-end binary spectrum by `lookahead` blocks, :536-543
+            uint32_t prev = 0;
+            const bool mine = lane >= 1 && lane < near_size;
+            if (mine) prev = e->near_hist[lane - 1];
+            __syncwarp();
+            if (mine) e->near_hist[lane] = prev;
+            if (lane == 0) e->near_hist[0] = near_bits;
+            __syncwarp();
+            near_bits = e->near_hist[e->lookahead];
+        }
+    }
     int key = 0x7fffffff, worst = 0, any_far = 0;
 #pragma unroll
     for (int p = 0; p < 4; p++) {
@@ -118,7 +139,77 @@ __device__ __forceinline__ void process_binary_spectrum(AecmInstanceState *st, u
         if (minimum_probability > thr) minimum_probability = thr;
     }
     last_delay_probability++;  // :608
-    const bool valid = depth > 1024 && (best < minimum_probability || best < last_delay_probability);
+    bool valid = depth > 1024 && (best < minimum_probability || best < last_delay_probability);
+    if (kExt) {
+        constexpr float kQ14 = 1.f / 16384.f;
+        int hits = e->candidate_hits, last_cand = e->last_candidate, compare = e->compare_delay;
+        float ldh = e->last_delay_histogram;
+        const int robust = e->robust, allowed = e->allowed_offset;
+        __syncwarp();  // the smoothed bit counts written above are read across lanes below; nobody writes the scalars before all have read them
+        if (any_far) {  // UpdateRobustValidationStatistics, :96-154
+            const float depth_f = __fmul_rn(__int2float_rn(depth), kQ14);
+            float decrease = depth_f;
+            const int max_hits = cand < last_delay ? 10 : 1000;  // :101-103
+            if (cand != last_cand) {  // :108-111
+                hits = 0;
+                last_cand = cand;
+            }
+            hits++;
+            if (hits < max_hits) decrease = __fmul_rn(__int2float_rn(st->mean_bit_counts[compare] - best), kQ14);  // :132-136
+#pragma unroll
+            for (int p = 0; p < 4; p++) {
+                const int i = lane + 32 * p;
+                if (i < AECM_MAX_DELAY) {
+                    float h = e->histogram[i];
+                    if (i == cand) {  // :119-122
+                        h = __fadd_rn(h, depth_f);
+                        if (h > 3000.f) h = 3000.f;
+                    }
+                    const int in_last = i >= last_delay - 2 && i <= last_delay + 1 && i != cand;  // :141-144
+                    const int in_cand = i >= cand - 2 && i <= cand + 1;
+                    const float dec = __fadd_rn(__fmul_rn(decrease, __int2float_rn(in_last)),
+                                                __fmul_rn(depth_f, __int2float_rn(!in_last && !in_cand)));
+                    h = __fsub_rn(h, dec);
+                    if (h < 0.f) h = 0.f;
+                    e->histogram[i] = h;
+                }
+            }
+            __syncwarp();
+        }
+        const float h_cand = e->histogram[cand], h_cmp = e->histogram[compare];
+        if (robust) {  // HistogramBasedValidation :178-225, RobustValidation :245-266
+            float fraction = 1.f;
+            const int diff = cand - last_delay;
+            if (diff > allowed) {
+                fraction = __fsub_rn(1.f, __fmul_rn(0.05f, __int2float_rn(diff - allowed)));
+                fraction = fraction > 0.5f ? fraction : 0.5f;
+            } else if (diff < 0) {
+                fraction = __fsub_rn(0.25f, __fmul_rn(0.05f, __int2float_rn(diff)));
+                fraction = fraction > 1.f ? 1.f : fraction;
+            }
+            float thr = __fmul_rn(h_cmp, fraction);
+            thr = thr > 1.5f ? thr : 1.5f;
+            const bool by_hist = h_cand >= thr && hits > 10;
+            bool ok = last_delay < 0 && (valid || by_hist);
+            ok |= valid && by_hist;
+            ok |= by_hist && h_cand > ldh;
+            valid = ok;
+        }
+        __syncwarp();  // every lane has read the histogram bins it needs
+        if (any_far && valid) {  // :643-661
+            if (cand != last_delay) {
+                ldh = h_cand > 250.f ? 250.f : h_cand;
+                if (h_cand < h_cmp && lane == 0) e->histogram[compare] = h_cand;
+            }
+            compare = cand;
+        }
+        if (lane == 0) {
+            e->candidate_hits = hits;
+            e->last_candidate = last_cand;
+            e->compare_delay = compare;
+            e->last_delay_histogram = ldh;
+        }
+    }
     if (any_far && valid) {  // :643-661
         last_delay = cand;
         if (best < last_delay_probability) last_delay_probability = best;
@@ -130,6 +221,7 @@ __device__ __forceinline__ void process_binary_spectrum(AecmInstanceState *st, u
 // memory starting at in_rd / clean_rd; the first out_n samples of the output block are appended to the output
 // FIFO at index out_wr (WebRtc_WriteBuffer of aecm_core.cc:554).
 // ------------------------------------------------------------------------------------------------
+template <bool kExt>
 __device__ __forceinline__ void process_block(const Ctx &c, int in_rd, int clean_rd, bool use_clean, int out_wr, int out_n) {
     AecmInstanceState *st = c.st;
     WarpScratch *sc = c.sc;
@@ -207,7 +299,7 @@ __device__ __forceinline__ void process_block(const Ctx &c, int in_rd, int clean
     int minimum_probability = S.minimum_probability, last_delay_probability = S.last_delay_probability;
     int last_delay = S.last_delay;
     __syncwarp();
-    process_binary_spectrum(st, near_bits, head, lane, minimum_probability, last_delay_probability, last_delay);
+    process_binary_spectrum<kExt>(c, near_bits, head, minimum_probability, last_delay_probability, last_delay);
     const int delay = last_delay == -2 ? 0 : last_delay;  // aecm_core_c.cc:479-483
     // the energy/VAD section below needs these old values; read them before the first commit
     const int lh = (S.log_head + AECM_LOG_RING - 1) & (AECM_LOG_RING - 1);

@@ -33,6 +33,7 @@ __device__ __forceinline__ bool word_aligned(const void *p) { return (reinterpre
 // L2: one 80-sample frame (aecm_core.cc:501-572).  The far frame comes from the HBM jitter FIFO (far_idx >= 0:
 // index of its first sample) or from the replay buffer farend_old[slot]; near/clean come from the input planes.
 // ------------------------------------------------------------------------------------------------
+template <bool kExt>
 __device__ __forceinline__ void process_frame(const Ctx &c, int far_idx, int slot, const int16_t *near80,
                                               const int16_t *clean80, int16_t *out80) {
     AecmInstanceState *st = c.st;
@@ -95,7 +96,7 @@ __device__ __forceinline__ void process_frame(const Ctx &c, int far_idx, int slo
         if (S.frm_in_cnt >= AECM_PART_LEN) {
             {
                 const int o_rd = S.frm_out_rd, o_cnt = S.frm_out_cnt;
-                process_block(c, S.frm_in_rd, S.frm_clean_rd, clean80 != nullptr, wrap_add(o_rd, o_cnt, AECM_FRM_RING),
+                process_block<kExt>(c, S.frm_in_rd, S.frm_clean_rd, clean80 != nullptr, wrap_add(o_rd, o_cnt, AECM_FRM_RING),
                               min(AECM_PART_LEN, AECM_FRM_RING - o_cnt));
             }
             int i_rd = S.frm_in_rd, i_cnt = S.frm_in_cnt, c_rd = S.frm_clean_rd, c_cnt = S.frm_clean_cnt;
@@ -201,6 +202,7 @@ __device__ __forceinline__ void est_buf_delay(DelayRegs &d, int ms, int mult) {
     if (d.time_for_delay_change > 25) d.known_delay = max(d.filt_delay - 160, 0);  // never forwarded (:390-391)
 }
 
+template <bool kExt>
 __device__ __forceinline__ int api_process(const Ctx &c, const int16_t *near_noisy, const int16_t *near_clean,
                                            int16_t *out, int n, int ms) {
     AecmScalars &S = c.st->s;
@@ -282,7 +284,7 @@ __device__ __forceinline__ int api_process(const Ctx &c, const int16_t *near_noi
             }
             __syncwarp();
         }
-        process_frame(c, far_idx, i, near_noisy + AECM_FRAME_LEN * i,
+        process_frame<kExt>(c, far_idx, i, near_noisy + AECM_FRAME_LEN * i,
                       near_clean ? near_clean + AECM_FRAME_LEN * i : nullptr, out + AECM_FRAME_LEN * i);
     }
     return ret;

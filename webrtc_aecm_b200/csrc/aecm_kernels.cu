@@ -82,6 +82,7 @@ __device__ __forceinline__ void bulk_store_record(AecmInstanceState *dst_gmem, c
 
 // shared memory: kWarpsPerCta x (AecmInstanceState, WarpScratch).  Persistent: warp w of CTA b owns the rows
 // b * kWarpsPerCta + w + k * (warps in the grid), k = 0, 1, ...; the mbarriers of its record buffer flip phase per row.
+template <bool kExt>
 __global__ void __launch_bounds__(kWarpsPerCta * 32, kCtasPerSm) aecm_call_kernel(AecmBatchPlanes planes, AecmCallArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -168,6 +169,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, kCtasPerSm) aecm_call_kerne
         c.far_ring_base = planes.far_ring;
         c.inst = inst;
         c.lane = lane;
+        c.ext = kExt ? planes.dly_ext + inst : nullptr;
 
         // (through the lane's own shared-memory word: the clamped value would otherwise be hoisted out of the call loop and,
         // with no register left for it, spilled to local memory)
@@ -188,7 +190,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, kCtasPerSm) aecm_call_kerne
                 if (status == 0) status = r;
             }
             if (a.near_noisy) {
-                const int r = api_process(c, a.near_noisy + o, use_clean ? a.near_clean + o : nullptr, a.out + o,
+                const int r = api_process<kExt>(c, a.near_noisy + o, use_clean ? a.near_clean + o : nullptr, a.out + o,
                                           a.samples_per_call, *my_ms);
                 if (status == 0) status = r;
             }
@@ -207,6 +209,34 @@ __global__ void aecm_init_kernel(AecmBatchPlanes planes, int first, int count, i
     const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (row >= count) return;
     init_instance(planes.state + first + row, fs, lane);
+    init_delay_ext(planes.dly_ext + first + row, lane);
+}
+
+// SURVEY 8-f4 control kernels, one warp per instance, straight on the HBM records
+__global__ void aecm_dly_options_kernel(AecmBatchPlanes planes, int first, int count, int robust, int allowed_offset,
+                                        int max_lookahead, int lookahead, int32_t *status) {
+    const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (row >= count) return;
+    AecmInstanceState *g = planes.state + first + row;
+    int r;
+    if (g->s.init_flag != AECM_INIT_MAGIC) r = AECM_UNINITIALIZED_ERROR;  // the estimator's state belongs to an initialised core
+    else r = set_delay_options(g, planes.dly_ext + first + row, robust, allowed_offset, max_lookahead, lookahead, lane);
+    if (status && lane == 0) status[row] = r;
+}
+
+__global__ void aecm_dly_soft_reset_kernel(AecmBatchPlanes planes, int first, int count, int delay_shift, int32_t *applied) {
+    const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (row >= count) return;
+    const int r = soft_reset_delay_estimator(planes.state + first + row, planes.dly_ext + first + row, delay_shift, lane);
+    if (applied && lane == 0) applied[row] = r;
+}
+
+__global__ void aecm_dly_query_kernel(AecmBatchPlanes planes, int first, int count, int32_t *last_delay, float *quality) {
+    const int row = blockIdx.x * blockDim.x + threadIdx.x;
+    if (row >= count) return;
+    const AecmInstanceState *g = planes.state + first + row;
+    if (last_delay) last_delay[row] = g->s.last_delay;
+    if (quality) quality[row] = last_delay_quality(g, planes.dly_ext + first + row);
 }
 
 __global__ void aecm_set_config_kernel(AecmBatchPlanes planes, int first, int count, int cng_mode, int echo_mode,
@@ -359,6 +389,29 @@ int aecm_cuda_launch_init_echo_path(const AecmBatchPlanes *p, int first, int cou
     return (int)cudaGetLastError();
 }
 
+int aecm_cuda_launch_dly_options(const AecmBatchPlanes *p, int first, int count, int robust, int allowed_offset, int max_lookahead,
+                                 int lookahead, int32_t *status, void *stream) {
+    if (count <= 0) return 0;
+    aecm_dly_options_kernel<<<(count + 3) / 4, 128, 0, static_cast<cudaStream_t>(stream)>>>(*p, first, count, robust, allowed_offset,
+                                                                                            max_lookahead, lookahead, status);
+    g_launches++;
+    return (int)cudaGetLastError();
+}
+
+int aecm_cuda_launch_dly_soft_reset(const AecmBatchPlanes *p, int first, int count, int delay_shift, int32_t *applied, void *stream) {
+    if (count <= 0) return 0;
+    aecm_dly_soft_reset_kernel<<<(count + 3) / 4, 128, 0, static_cast<cudaStream_t>(stream)>>>(*p, first, count, delay_shift, applied);
+    g_launches++;
+    return (int)cudaGetLastError();
+}
+
+int aecm_cuda_launch_dly_query(const AecmBatchPlanes *p, int first, int count, int32_t *last_delay, float *quality, void *stream) {
+    if (count <= 0) return 0;
+    aecm_dly_query_kernel<<<(count + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(*p, first, count, last_delay, quality);
+    g_launches++;
+    return (int)cudaGetLastError();
+}
+
 int aecm_cuda_launch_call(const AecmBatchPlanes *p, const AecmCallArgs *a, void *stream) {
     if (a->count <= 0 || a->n_calls <= 0) return 0;
     static std::atomic<bool> attr_set[64];  // function attributes are per device
@@ -366,10 +419,13 @@ int aecm_cuda_launch_call(const AecmBatchPlanes *p, const AecmCallArgs *a, void 
     int dev = 0;
     if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return (int)cudaErrorInvalidDevice;
     if (!attr_set[dev]) {
-        cudaError_t e = cudaFuncSetAttribute(aecm_call_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return (int)e;
-        e = cudaFuncSetAttribute(aecm_call_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-        if (e != cudaSuccess) return (int)e;
+        for (int v = 0; v < 2; v++) {
+            const void *fn = v ? (const void *)aecm_call_kernel<true> : (const void *)aecm_call_kernel<false>;
+            cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e != cudaSuccess) return (int)e;
+            e = cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+            if (e != cudaSuccess) return (int)e;
+        }
         attr_set[dev] = true;
     }
     static std::atomic<int> sm_count[64];  // persistent grid: at most (resident CTAs per SM) x (SMs) CTAs
@@ -380,7 +436,8 @@ int aecm_cuda_launch_call(const AecmBatchPlanes *p, const AecmCallArgs *a, void 
         sm_count[dev] = n;
     }
     const int blocks = std::min((a->count + kWarpsPerCta - 1) / kWarpsPerCta, sm_count[dev] * kCtasPerSm);
-    aecm_call_kernel<<<blocks, kWarpsPerCta * 32, smem, static_cast<cudaStream_t>(stream)>>>(*p, *a);
+    if (a->ext) aecm_call_kernel<true><<<blocks, kWarpsPerCta * 32, smem, static_cast<cudaStream_t>(stream)>>>(*p, *a);
+    else aecm_call_kernel<false><<<blocks, kWarpsPerCta * 32, smem, static_cast<cudaStream_t>(stream)>>>(*p, *a);
     g_launches++;
     return (int)cudaGetLastError();
 }

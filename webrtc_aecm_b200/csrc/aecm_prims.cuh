@@ -144,6 +144,7 @@ struct Ctx {
     int16_t *far_ring_base;
     int inst;
     int lane;
+    AecmDelayExt *ext;      // SURVEY 8-f4 record of this instance in HBM (kExt instantiation only; otherwise unused)
     // the record in HBM (write-through target of the fields that are not bulk-stored back)
     __device__ __forceinline__ AecmInstanceState *g() const { return state_base + inst; }
     // this instance's 100 x 66 rows in HBM

@@ -107,6 +107,22 @@ typedef struct {
     int16_t frm_clean[AECM_FRM_RING];
 } AecmInstanceState;
 
+/* the delay estimator's optional machinery -- robust validation (float histogram of candidate delays,
+ * delay_estimator.cc:96-266), near-end lookahead (:536-543) and soft reset (:336-367, 506-519) -- which AECM leaves at
+ * its Create-time defaults (aecm_core.cc:218, 225).  Kept in a plane of its own, touched only by the launches of a
+ * batch on which AecmB200_SetDelayEstimatorOptions / AecmB200_SoftResetDelayEstimator has been called (they run the
+ * kExt instantiation of the call kernel, straight on this HBM record); the default path never reads it. */
+#define AECM_MAX_LOOKAHEAD 15
+typedef struct {
+    float histogram[AECM_MAX_DELAY + 4];   /* [100] is the dummy bin used while last_delay == -2 (delay_estimator.cc:459-461) */
+    uint32_t near_hist[AECM_MAX_LOOKAHEAD + 1]; /* binary_near_history, newest first */
+    /* properties of the estimator OBJECT: survive Init (delay_estimator.cc:428-433, delay_estimator_wrapper.cc:384-434) */
+    int32_t robust, allowed_offset, lookahead, near_size; /* near_size 0 (a fresh batch) means 1 = max_lookahead 0 */
+    /* robust-validation statistics, reset by Init (delay_estimator.cc:499-503) */
+    int32_t candidate_hits, last_candidate, compare_delay;
+    float last_delay_histogram;
+} AecmDelayExt;
+
 /* bytes of part A (multiple of 16) */
 #define AECM_STATE_PART_A ((int)(sizeof(AecmScalars) + 2 * AECM_FRAME_LEN * 2 + 3 * AECM_FRM_RING * 2 + 2 * 64 * 2))
 #define AECM_STATE_BYTES ((int)sizeof(AecmInstanceState))
@@ -130,6 +146,7 @@ typedef struct {
     AecmInstanceState *state;
     uint16_t *far_hist;
     int16_t *far_ring;
+    AecmDelayExt *dly_ext;
     int32_t n_instances;
 } AecmBatchPlanes;
 
@@ -148,6 +165,7 @@ typedef struct {
     int32_t ms_uniform;
     int32_t mask_stride;    /* entries between consecutive calls in far_mask (>= count) */
     const int32_t *index;   /* optional [count]: plane row r belongs to instance index[r] (distinct); `first` unused */
+    int32_t ext;            /* != 0: run the instantiation that drives the delay estimator's optional machinery (AecmDelayExt) */
 } AecmCallArgs;
 
 /* all return a cudaError_t value (0 = success); launches are asynchronous on `stream` */
@@ -157,6 +175,11 @@ int aecm_cuda_launch_set_config(const AecmBatchPlanes *p, int first, int count, 
 int aecm_cuda_launch_init_echo_path(const AecmBatchPlanes *p, int first, int count, const int16_t *d_path,
                                     int path_stride, int32_t *status, void *stream);
 int aecm_cuda_launch_call(const AecmBatchPlanes *p, const AecmCallArgs *a, void *stream);
+/* SURVEY 8-f4 control kernels; robust/allowed_offset/max_lookahead/lookahead as in AecmB200_SetDelayEstimatorOptions */
+int aecm_cuda_launch_dly_options(const AecmBatchPlanes *p, int first, int count, int robust, int allowed_offset, int max_lookahead,
+                                 int lookahead, int32_t *status, void *stream);
+int aecm_cuda_launch_dly_soft_reset(const AecmBatchPlanes *p, int first, int count, int delay_shift, int32_t *applied, void *stream);
+int aecm_cuda_launch_dly_query(const AecmBatchPlanes *p, int first, int count, int32_t *last_delay, float *quality, void *stream);
 long long aecm_cuda_selftest_sqrt(uint32_t first, uint32_t count);
 int aecm_cuda_selftest_fft(int mode, const int16_t *in, int16_t *out, int32_t *scale, int n); /* host arrays */
 int aecm_cuda_kernel_launch_count(void); /* kernels launched so far by this translation unit */
