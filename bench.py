@@ -249,6 +249,11 @@ def run_ours(args):
             dist.all_reduce(t, op=dist.ReduceOp.SUM)
         return float(t.item())
 
+    host_ranks = [numa]
+    if world > 1:  # every rank's placement goes into the line: the 8-GPU end-to-end number depends on it
+        host_ranks = [None] * world
+        dist.all_gather_object(host_ranks, numa)
+
     sampler = ClockSampler(local)
     sampler.start()  # early: nvidia-smi takes about a second before its first sample
     batch = AecmBatch(B, local)
@@ -486,7 +491,7 @@ def run_ours(args):
             "config": config_dict(args, world),
             "blocks_per_instance_per_step": blocks_per_inst / K, "realtime_channels": value / (250.0 if fs == 16000 else 125.0),
             "parity_checked": parity["bit_exact"] if parity else 0, "parity": parity,
-            "clocks": clocks, "gpu_launches": int(launches), "host": numa,
+            "clocks": clocks, "gpu_launches": int(launches), "host": numa, "host_ranks": host_ranks if world > 1 else None,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "traffic_unit": "bytes per launch (ncu dram__bytes_read.sum + dram__bytes_write.sum)",
                          "traffic_gbs": traffic / kernel_s / 1e9 if traffic else None,

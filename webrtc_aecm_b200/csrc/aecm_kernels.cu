@@ -14,6 +14,7 @@
 #include <algorithm>
 #include <atomic>
 #include <cstddef>
+#include <cstdlib>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -435,7 +436,14 @@ int aecm_cuda_launch_call(const AecmBatchPlanes *p, const AecmCallArgs *a, void 
         if (e != cudaSuccess || n <= 0) return (int)(e != cudaSuccess ? e : cudaErrorInvalidDevice);
         sm_count[dev] = n;
     }
-    const int blocks = std::min((a->count + kWarpsPerCta - 1) / kWarpsPerCta, sm_count[dev] * kCtasPerSm);
+    // AECM_B200_MAX_CTAS caps the persistent grid (diagnostics: with 1, a batch of 70 instances walks three rows per warp,
+    // the last one partial, under compute-sanitizer in seconds)
+    static const int max_ctas = [] {
+        const char *e = getenv("AECM_B200_MAX_CTAS");
+        const int v = e ? atoi(e) : 0;
+        return v > 0 ? v : 1 << 30;
+    }();
+    const int blocks = std::min(std::min((a->count + kWarpsPerCta - 1) / kWarpsPerCta, sm_count[dev] * kCtasPerSm), max_ctas);
     if (a->ext) aecm_call_kernel<true><<<blocks, kWarpsPerCta * 32, smem, static_cast<cudaStream_t>(stream)>>>(*p, *a);
     else aecm_call_kernel<false><<<blocks, kWarpsPerCta * 32, smem, static_cast<cudaStream_t>(stream)>>>(*p, *a);
     g_launches++;

@@ -123,8 +123,10 @@ def bind_to_gpu(device_index: int, world: int = 1) -> dict:
         info["cpu_binding"] = f"{len(usable)} GPU-local CPUs"
     elif usable:
         info["cpu_binding"] = f"unchanged: all {len(allowed)} allowed CPUs are GPU-local"
-    else:
+    elif local:
         info["cpu_binding"] = "unchanged: none of the allowed CPUs is GPU-local (cpuset confines the process to another socket)"
+    else:
+        info["cpu_binding"] = "unchanged: the GPU's local CPUs are unknown (no sysfs entry / no NVML)"
     info["numa_bound_cpus"] = len(os.sched_getaffinity(0))
     if node >= 0 and (not mems or node in mems) and len(nodes) > 1:
         err = prefer_memory_node(node)
