@@ -45,3 +45,34 @@ def test_gpu_arm_refuses_to_run_without_a_device():
         pytest.skip("a GPU is present")
     r = run_bench("--steps", "2", "--warmup", "1")
     assert r.returncode != 0 and "no CUDA device" in (r.stderr + r.stdout)
+
+
+def test_both_arms_describe_the_same_workload():
+    """The driver compares the two arms' `config` dicts (`same_config`): both come from one function of the command line.
+    Default = BASELINE configs[3], 262144 instances strong-scaled over the GPUs of the run."""
+    import argparse
+    import importlib.util
+
+    spec = importlib.util.spec_from_file_location("bench", os.path.join(ROOT, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    argv, sys.argv = sys.argv, ["bench.py"]
+    try:
+        spec.loader.exec_module(bench)
+        for n in (1, 2, 4, 8):
+            sys.argv = ["bench.py", "--gpus", str(n), "--steps", "20", "--warmup", "5"]
+            a = bench.parse_args()
+            cfg = bench.config_dict(a, n)
+            assert cfg["total_batch"] == 262144 and cfg["batch_per_gpu"] == 262144 // n and cfg["scaling"] == "strong"
+            assert "configs[3]" in cfg["workload"] and "model" not in cfg
+            assert bench.workload(a, n) == (262144 // n, "strong")
+        sys.argv = ["bench.py", "--batch", "4096", "--gpus", "2"]
+        assert bench.workload(bench.parse_args(), 2) == (4096, "weak")
+    finally:
+        sys.argv = argv
+    r = run_bench("--impl", "reference", "--steps", "2", "--warmup", "1", "--total-batch", "128")
+    d = json.loads(r.stdout.strip().splitlines()[-1])
+    sys.argv = ["bench.py", "--steps", "2", "--warmup", "1", "--total-batch", "128"]
+    try:
+        assert d["config"] == bench.config_dict(bench.parse_args(), 1)
+    finally:
+        sys.argv = argv

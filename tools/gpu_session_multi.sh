@@ -36,9 +36,5 @@ PY
 import json
 d=json.loads(open('gpurun_out/m8_bench_n$n.json').read().strip().splitlines()[-1]); print('N=$n value %.4g e2e %.4g link %s'%(d['value'], d['e2e']['value'], d['e2e']['host_link_gbs']))"
   done
-  timeout 900 python bench.py --gpus 1 --steps 20 --warmup 5 --no-realtime --no-cpu-baseline > gpurun_out/m8_bench_n1.json 2> gpurun_out/m8_bench_n1.err
-  python -c "
-import json
-d=json.loads(open('gpurun_out/m8_bench_n1.json').read().strip().splitlines()[-1]); print('N=1 value %.4g e2e %.4g link %s'%(d['value'], d['e2e']['value'], d['e2e']['host_link_gbs']))"
 fi
 ls gpurun_out | grep "^m${N}"

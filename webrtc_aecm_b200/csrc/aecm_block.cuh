@@ -55,8 +55,9 @@ __device__ __forceinline__ void time_to_frequency(const Ctx &c, const int16_t *c
             const int im = (i == 0 || i == 64) ? 0 : s16(-bim[n][p]);  // :188-190, :296-297
             // :305-358.  The reference short-cuts re == 0 / im == 0 to |im| / |re| (as uint16, so |-32768| = 32768);
             // floor(sqrt(v*v)) = |v| exactly, so the general formula (with the AddSatW32 clamp) covers all three cases.
+            // Bin 64 (p == 2, im == 0) IS the short cut: |re|, no root needed (only lane 0's value is kept).
             const uint32_t e = (uint32_t)(re * re) + (uint32_t)(im * im);
-            const int mag = sqrt_floor((int)min(e, 0x7fffffffu));
+            const int mag = p < 2 ? sqrt_floor((int)min(e, 0x7fffffffu)) : abs(re);
             if (p < 2 || lane == 0) {
                 mag_out[n][i] = (uint16_t)mag;
                 if (cplx_out[n]) cplx_out[n][i] = pack16(re, im);
