@@ -29,6 +29,25 @@ __device__ __forceinline__ int fifo_move(int &rd, int &cnt, int cap, int k) {  /
 // ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ bool word_aligned(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 3) == 0; }
 
+// CTA-wide rendezvous points that keep the warps of an SM on the same stretch of code (the call path is 110 KB of
+// straight-line SASS against a 32 KB instruction cache).  They sit at fixed places of a call -- before every frame and
+// before every potential block -- so every warp of the CTA passes the same number of them per call; a warp whose instance
+// does nothing in this call (un-initialised, start-up phase) or that has no row walks through them with idle_call().
+__device__ __forceinline__ void cta_rendezvous_frame() {
+    if (kSyncPoints >= 1) __syncthreads();
+}
+__device__ __forceinline__ void cta_rendezvous_block() {
+    if (kSyncPoints >= 2) __syncthreads();
+}
+__device__ __forceinline__ void idle_call(int n_frames) {
+    if (kSyncPoints >= 1)
+        for (int i = 0; i < n_frames; i++) {
+            cta_rendezvous_frame();
+            cta_rendezvous_block();
+            cta_rendezvous_block();
+        }
+}
+
 // ------------------------------------------------------------------------------------------------
 // L2: one 80-sample frame (aecm_core.cc:501-572).  The far frame comes from the HBM jitter FIFO (far_idx >= 0:
 // index of its first sample) or from the replay buffer farend_old[slot]; near/clean come from the input planes.
@@ -93,6 +112,7 @@ __device__ __forceinline__ void process_frame(const Ctx &c, int far_idx, int slo
     // :527-555 "while (available >= PART_LEN)": a FIFO below 64 gains 80 samples, so at most two blocks per frame
 #pragma unroll 1
     for (int blk = 0; blk < 2; blk++) {
+        cta_rendezvous_block();
         if (S.frm_in_cnt >= AECM_PART_LEN) {
             {
                 const int o_rd = S.frm_out_rd, o_cnt = S.frm_out_cnt;
@@ -209,7 +229,10 @@ __device__ __forceinline__ int api_process(const Ctx &c, const int16_t *near_noi
     const int lane = c.lane;
     const int n_frames = n / AECM_FRAME_LEN;
     int ret = 0;
-    if (S.init_flag != AECM_INIT_MAGIC) return AECM_UNINITIALIZED_ERROR;  // :264
+    if (S.init_flag != AECM_INIT_MAGIC) {  // :264
+        idle_call(n_frames);
+        return AECM_UNINITIALIZED_ERROR;
+    }
     {
         if (ms < 0) { ms = 0; ret = AECM_BAD_PARAMETER_WARNING; }          // :272-278
         else if (ms > 500) { ms = 500; ret = AECM_BAD_PARAMETER_WARNING; }
@@ -258,10 +281,12 @@ __device__ __forceinline__ int api_process(const Ctx &c, const int16_t *near_noi
                 S.far_rd = far_rd; S.far_cnt = far_cnt;
             }
             __syncwarp();
+            idle_call(n_frames);
             return ret;
         }
     }
     for (int i = 0; i < n_frames; i++) {  // :358-397
+        cta_rendezvous_frame();
         int far_idx = -2;  // "replay farend_old" (even, so that the word-wide mover still applies)
         {  // wrapper bookkeeping of this frame on register copies, committed before the frame is processed
             DelayRegs d;

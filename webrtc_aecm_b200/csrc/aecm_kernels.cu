@@ -111,8 +111,14 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, kCtasPerSm) aecm_call_kerne
         const int row = *my_row;
         if (row - warp >= a.count) break;  // the CTA's rows are exhausted (same trip count for all its warps)
         *my_row = row + stride;
-        if (kRowResync && row - warp != (int)blockIdx.x * kWarpsPerCta) __syncthreads();
-        if (row >= a.count) continue;
+        if (kRowResync && row - warp != (int)blockIdx.x * kWarpsPerCta &&
+            (AECM_ROW_RESYNC == 1 || ((row - warp) / stride) % AECM_ROW_RESYNC == 0))
+            __syncthreads();  // (AECM_ROW_RESYNC = k > 1: only before every k-th row; measured)
+        if (row >= a.count) {  // no row left for this warp in the CTA's last pass: keep the CTA's rendezvous count
+            if (a.near_noisy)
+                for (int call = 0; call < a.n_calls; call++) idle_call(a.samples_per_call / AECM_FRAME_LEN);
+            continue;
+        }
         // (derived from the volatile row word on purpose: otherwise the compiler hoists the per-lane prefetch offsets and
         // predicates out of the row loop and, with no register to keep them in, spills them to local memory)
         const int row_bytes = (a.samples_per_call + (row < 0 ? 1 : 0)) * (int)sizeof(int16_t);
@@ -121,6 +127,8 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, kCtasPerSm) aecm_call_kerne
             inst = __ldg(&a.index[row]);
             if ((unsigned)inst >= (unsigned)planes.n_instances) {
                 if (a.status) a.status[row] = AECM_BAD_PARAMETER_ERROR;  // (every lane, same word: rare path, no lane test to keep)
+                if (a.near_noisy)
+                    for (int call = 0; call < a.n_calls; call++) idle_call(a.samples_per_call / AECM_FRAME_LEN);
                 continue;
             }
         }

@@ -32,6 +32,13 @@ constexpr int kCtasPerSm = kWarpsPerCta >= 28 ? 1 : 28 / kWarpsPerCta;
 #define AECM_ROW_RESYNC 1
 #endif
 constexpr bool kRowResync = AECM_ROW_RESYNC != 0;
+// Finer rendezvous points inside a row: 1 = also before every 80-sample frame, 2 = also before every (potential) 64-sample
+// block.  Every warp of the CTA executes the same number of them per call whatever its instance is doing (start-up,
+// un-initialised, no row at all): see cta_rendezvous_* in aecm_frame_api.cuh.  Measured, DESIGN.md 4.1.
+#ifndef AECM_SYNC_POINTS
+#define AECM_SYNC_POINTS 0
+#endif
+constexpr int kSyncPoints = kRowResync ? AECM_SYNC_POINTS : 0;
 // MEASUREMENT ONLY (tools/run_variants.sh): 2 drops the one-live-lane pass for bin 64 from every 65-bin loop.  The output
 // is then WRONG; the build exists to bound what removing that pass could buy.  The product is built with 3.
 #ifndef AECM_BIN_PASSES
