@@ -171,6 +171,68 @@ class ClockSampler:
                 "samples": len(inside), "note": note}
 
 
+class NvmlSampler:
+    """SM clock and throttle reasons read through NVML from a thread of this process every millisecond: at 8 GPUs the timed
+    region of a 20-step run is a few milliseconds, shorter than anything nvidia-smi can sample.  Same interface as
+    ClockSampler, which remains the fall-back when NVML is not usable."""
+    REASONS = [("hw_slowdown", 0x8), ("hw_thermal_slowdown", 0x40), ("sw_thermal_slowdown", 0x20), ("sw_power_cap", 0x4)]
+
+    def __init__(self, gpu_index: int):
+        self.gpu = gpu_index
+        self.rows = []
+        self.thread = None
+        self.stop = False
+        self.fallback = None
+
+    def start(self):
+        try:
+            import pynvml
+
+            pynvml.nvmlInit()
+            idx = self.gpu
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES", "")
+            if vis and all(p.strip().isdigit() for p in vis.split(",")):
+                idx = int(vis.split(",")[self.gpu])
+            h = pynvml.nvmlDeviceGetHandleByIndex(idx)
+            mx = float(pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM))
+            get_reasons = getattr(pynvml, "nvmlDeviceGetCurrentClocksEventReasons", None) or pynvml.nvmlDeviceGetCurrentClocksThrottleReasons
+            get_reasons(h)
+            float(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM))
+        except Exception:  # no NVML in this environment: the nvidia-smi sampler
+            self.fallback = ClockSampler(self.gpu)
+            self.fallback.start()
+            return
+
+        def loop():
+            while not self.stop:
+                try:
+                    self.rows.append((time.time(), float(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)), mx, int(get_reasons(h))))
+                except Exception:
+                    pass
+                time.sleep(0.001)
+
+        self.thread = threading.Thread(target=loop, daemon=True)
+        self.thread.start()
+
+    def window(self, t0: float, t1: float):
+        if self.fallback is not None:
+            return self.fallback.window(t0, t1)
+        self.stop = True
+        self.thread.join(timeout=2)
+        rows = list(self.rows)
+        inside = [r for r in rows if t0 <= r[0] <= t1]
+        note = "NVML samples inside the timed region (1 ms period)"
+        if not inside and rows:
+            inside = [min(rows, key=lambda r: abs(r[0] - 0.5 * (t0 + t1)))]
+            note = "no NVML sample fell inside the timed region: nearest sample"
+        bits = 0
+        for r in inside:
+            bits |= r[3]
+        return {"sm_mhz": float(np.median([r[1] for r in inside])) if inside else None,
+                "sm_max_mhz": max(r[2] for r in inside) if inside else None,
+                "reasons": [n for n, m in self.REASONS if bits & m], "samples": len(inside), "note": note}
+
+
 class HostPlanes:
     """Pinned host memory from the library's own allocator (cudaMallocHost), viewed as numpy int16 arrays.  First touched
     by the calling thread, which bench.py has bound to the GPU's NUMA node."""
@@ -254,8 +316,8 @@ def run_ours(args):
         host_ranks = [None] * world
         dist.all_gather_object(host_ranks, numa)
 
-    sampler = ClockSampler(local)
-    sampler.start()  # early: nvidia-smi takes about a second before its first sample
+    sampler = NvmlSampler(local)
+    sampler.start()  # (the nvidia-smi fall-back takes about a second before its first sample: start early)
     batch = AecmBatch(B, local)
     stream = torch.cuda.current_stream(dev)
     batch.adopt_cuda_stream(stream.cuda_stream)  # so torch.cuda.Event brackets exactly our launches

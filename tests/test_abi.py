@@ -102,6 +102,19 @@ def test_built_kernel_keeps_its_launch_shape_and_hardware_paths():
     assert not re.search(r"\b(LDL|STL)\b", call)
 
 
+def test_delay_estimator_example_builds(tmp_path):
+    """examples/delay_estimator_options.c (SURVEY 8-f4 from plain C) compiles warning-free against include/; it runs in the
+    GPU suite (tests/test_gpu_main_cc.py)."""
+    import subprocess
+
+    exe = str(tmp_path / "deo")
+    lib_dir = os.path.join(ROOT, "webrtc_aecm_b200")
+    r = subprocess.run(["gcc", "-O2", "-Wall", "-Wextra", "-Werror", "-I", os.path.join(ROOT, "include"),
+                        os.path.join(ROOT, "examples", "delay_estimator_options.c"), "-L", lib_dir, "-laecm_b200", f"-Wl,-rpath,{lib_dir}",
+                        "-o", exe], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+
+
 def test_example_program_builds_against_the_public_headers(tmp_path):
     """examples/batch_stream.c (the INTEGRATION.md throughput loop as a complete program) compiles warning-free against
     include/ and links against the library; without a GPU it must stop with the library's own refusal."""

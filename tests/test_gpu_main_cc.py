@@ -45,3 +45,24 @@ def test_main_cc_wav_pair_is_byte_identical(tmp_path, fs):
     assert len(outs["ref"]) == len(outs["b200"]) > 0
     assert outs["ref"] == outs["b200"]
     assert outs["ref"] != np.ascontiguousarray(near[0], dtype="<i2").tobytes()  # the canceller did act
+
+
+def test_c_examples_run_on_the_gpu(tmp_path):
+    """examples/*.c built against include/ and run on the device: the throughput loop of INTEGRATION.md and the delay
+    estimator's optional machinery (the estimate must find the synthetic echo delays, 3 ms = 0.75 blocks apart)."""
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    lib_dir = os.path.join(root, "webrtc_aecm_b200")
+    outs = {}
+    for name, args in (("batch_stream", ["512", "60"]), ("delay_estimator_options", [])):
+        exe = str(tmp_path / name)
+        r = subprocess.run(["gcc", "-O2", "-I", os.path.join(root, "include"), os.path.join(root, "examples", name + ".c"), "-L", lib_dir,
+                            "-laecm_b200", f"-Wl,-rpath,{lib_dir}", "-o", exe], capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr
+        run = subprocess.run([exe, *args], capture_output=True, text=True, timeout=300)
+        assert run.returncode == 0, (run.stdout, run.stderr)
+        outs[name] = run.stdout
+    lines = [l for l in outs["delay_estimator_options"].splitlines() if l.startswith("instance")]
+    assert len(lines) == 8
+    delays = [int(l.split("delay estimate")[1].split()[0]) for l in lines]
+    assert delays == sorted(delays) and delays[-1] > delays[0] >= 0, delays  # larger echo delay -> larger estimate
+    assert "soft reset by 2 blocks" in outs["delay_estimator_options"]

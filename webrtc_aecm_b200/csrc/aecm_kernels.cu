@@ -209,8 +209,9 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, kCtasPerSm) aecm_call_kerne
         bulk_store_record(c.g(), st, rec_bytes, stored_dirty, lane);
         if (lane == 0) {
             if (a.status) a.status[row] = status;
-            sc->phase ^= 1;  // ordered before the next row's reads by the __syncwarp of its bulk_load_record
+            sc->phase ^= 1;
         }
+        __syncwarp();  // the new parity is read by every lane at the top of the next row
     }
 }
 
