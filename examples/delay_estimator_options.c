@@ -21,7 +21,7 @@ int main(void) {
     int32_t status[N], delay[N], applied[N];
     float quality[N];
     uint32_t rng = 12345u;
-    int c, i, k, rc;
+    int c, i, k;
     if (!b) {
         fprintf(stderr, "AecmB200_Create failed: no CUDA device (this library has no CPU path)\n");
         return 1;
@@ -29,14 +29,27 @@ int main(void) {
     far = (int16_t *)AecmB200_HostAlloc((size_t)N * SPC * sizeof(int16_t));
     near = (int16_t *)AecmB200_HostAlloc((size_t)N * SPC * sizeof(int16_t));
     out = (int16_t *)AecmB200_HostAlloc((size_t)N * SPC * sizeof(int16_t));
-    if (!far || !near || !out) return 1;
-    if (AecmB200_Init(b, 0, N, 16000) || AecmB200_SetConfig(b, 0, N, cfg, status)) return 1;
-    /* right after Init, as the reference collects the validation statistics from Init on */
-    rc = AecmB200_SetDelayEstimatorOptions(b, 0, N, &opt, status);
-    if (rc) {
-        fprintf(stderr, "SetDelayEstimatorOptions -> %d (%s)\n", rc, AecmB200_LastError(b));
+#define CHECK(call)                                                                              \
+    do {                                                                                         \
+        const int32_t rc_ = (call);                                                              \
+        if (rc_) {                                                                               \
+            fprintf(stderr, "%s -> %d (%s)\n", #call, (int)rc_, AecmB200_LastError(b));         \
+            return 1;                                                                            \
+        }                                                                                        \
+    } while (0)
+    if (!far || !near || !out) {
+        fprintf(stderr, "AecmB200_HostAlloc failed\n");
         return 1;
     }
+    CHECK(AecmB200_Init(b, 0, N, 16000));
+    CHECK(AecmB200_SetConfig(b, 0, N, cfg, status));
+    /* right after Init, as the reference collects the validation statistics from Init on */
+    CHECK(AecmB200_SetDelayEstimatorOptions(b, 0, N, &opt, status));
+    for (i = 0; i < N; i++)
+        if (status[i]) {
+            fprintf(stderr, "SetDelayEstimatorOptions: instance %d refused with %d\n", i, (int)status[i]);
+            return 1;
+        }
     {
         static int16_t hist[N][SPC * 64]; /* far-end history for the synthetic echo: instance i hears the far end i*3 ms late */
         memset(hist, 0, sizeof(hist));
@@ -55,14 +68,14 @@ int main(void) {
             memset(&a, 0, sizeof(a));
             a.farend = far; a.nearendNoisy = near; a.out = out;
             a.rowStride = SPC; a.count = N; a.nrOfSamples = SPC; a.nCalls = 1; a.msUniform = 40; a.status = status;
-            if (AecmB200_ProcessStream(b, &a)) return 1;
+            CHECK(AecmB200_ProcessStream(b, &a));
             if (c == CALLS / 2) { /* the caller shifted its far-end stream by two blocks: tell the estimator */
-                if (AecmB200_SoftResetDelayEstimator(b, 0, N, 2, applied)) return 1;
+                CHECK(AecmB200_SoftResetDelayEstimator(b, 0, N, 2, applied));
                 printf("soft reset by 2 blocks: lookahead shift applied per instance = %d\n", applied[0]);
             }
         }
     }
-    if (AecmB200_GetDelayEstimate(b, 0, N, delay, quality)) return 1;
+    CHECK(AecmB200_GetDelayEstimate(b, 0, N, delay, quality));
     for (i = 0; i < N; i++) printf("instance %d: delay estimate %d blocks, quality %.3f\n", i, delay[i], quality[i]);
     AecmB200_HostFree(far); AecmB200_HostFree(near); AecmB200_HostFree(out);
     AecmB200_Free(b);

@@ -504,9 +504,19 @@ static int32_t enqueue_stream(AecmB200Batch *b, const AecmB200StreamArgs *h, Slo
     /* dense far plane immediately followed by the dense near plane: one DMA for both */
     adjacent = h->farend && h->nearendNoisy && pitch_src == pitch_dst && h->nearendNoisy == h->farend + rows * width;
     if (adjacent) {
-        CU(b, cudaMemcpyAsync(sl->d_far, h->farend, 2 * rows * pitch_dst, cudaMemcpyHostToDevice, sl->copy));
-        k.far = sl->d_far;
-    } else if (h->farend) {
+        /* Two planes that merely touch in the address space but come from two pinned allocations cannot be moved by one
+         * copy: the runtime refuses it up front (invalid value, nothing enqueued) and the planes go separately. */
+        const cudaError_t e = cudaMemcpyAsync(sl->d_far, h->farend, 2 * rows * pitch_dst, cudaMemcpyHostToDevice, sl->copy);
+        if (e == cudaErrorInvalidValue) {
+            (void)cudaGetLastError();
+            adjacent = 0;
+        } else if (e != cudaSuccess) {
+            return fail(b, "cudaMemcpyAsync(far|near)", e);
+        } else {
+            k.far = sl->d_far;
+        }
+    }
+    if (!adjacent && h->farend) {
         CU(b, copy_plane(sl->d_far, pitch_dst, h->farend, pitch_src, pitch_dst, rows, cudaMemcpyHostToDevice, sl->copy));
         k.far = sl->d_far;
     }
