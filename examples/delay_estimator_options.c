@@ -59,8 +59,10 @@ int main(void) {
                 const int d = i * 48; /* samples */
                 memmove(hist[i], hist[i] + SPC, sizeof(hist[i]) - SPC * sizeof(int16_t));
                 for (k = 0; k < SPC; k++) {
+                    /* bursty noise (a new level every 30 ms): the binary-spectrum estimator needs a far end that changes */
+                    static const int level[8] = {0, 8, 1, 6, 0, 3, 8, 2};
                     rng = rng * 1664525u + 1013904223u;
-                    hist[i][SPC * 63 + k] = (int16_t)((int32_t)(rng >> 16) - 32768) / 4;
+                    hist[i][SPC * 63 + k] = (int16_t)(((int32_t)(rng >> 16) - 32768) / 16 * level[(c / 3 + c / 7) & 7] / 2);
                     far[i * SPC + k] = hist[i][SPC * 63 + k];
                     near[i * SPC + k] = (int16_t)(hist[i][SPC * 63 + k - d] / 2);
                 }
