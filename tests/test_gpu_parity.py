@@ -654,3 +654,38 @@ def test_delay_estimator_options_fused_calls_error_codes_and_init_semantics():
     rc, out3, status = b.process_stream(far, near, samples_per_call=160, ms=ms)
     np.testing.assert_array_equal(out3, base)
     b.close()
+
+
+def test_far_and_near_planes_that_touch_but_are_two_pinned_allocations():
+    """A dense near plane that starts exactly where the dense far plane ends normally crosses PCIe in ONE transfer.  When the
+    two planes are separate pinned allocations that merely touch (two cudaMallocHost blocks can end up back to back, as
+    examples/delay_estimator_options.c found out), the runtime refuses a copy spanning both: the library must then move
+    them separately instead of failing the call."""
+    import torch
+
+    from webrtc_aecm_b200 import AecmBatch
+
+    fs, spc, n, calls = 16000, 160, 64, 12
+    plane = n * spc  # 20480 bytes = 5 pages
+    far_s, near_s = synth_streams(n, calls * spc, fs, seed=321, delay_ms=30)
+    want, _, _ = ol.run_streams(far_s, near_s, fs=fs, impl="oracle")
+    raw = np.zeros(2 * plane + 4096, dtype=np.int16)
+    off = (-raw.ctypes.data % 4096) // 2
+    far, near = raw[off:off + plane].reshape(n, spc), raw[off + plane:off + 2 * plane].reshape(n, spc)
+    assert near.ctypes.data == far.ctypes.data + plane * 2
+    rt = torch.cuda.cudart()
+    for a in (far, near):  # two registrations of two adjacent page ranges
+        assert int(rt.cudaHostRegister(a.ctypes.data, plane * 2, 0)) == 0
+    try:
+        b = AecmBatch(n, 0)
+        assert b.init(fs) == 0
+        for c in range(calls):
+            far[:] = far_s[:, c * spc:(c + 1) * spc]
+            near[:] = near_s[:, c * spc:(c + 1) * spc]
+            rc, out, status = b.process_stream(far, near, samples_per_call=spc)
+            assert rc == 0 and not status.any(), (rc, b._lib.AecmB200_LastError(b._h))
+            np.testing.assert_array_equal(out, want[:, c * spc:(c + 1) * spc])
+        b.close()
+    finally:
+        for a in (far, near):
+            rt.cudaHostUnregister(a.ctypes.data)
