@@ -137,7 +137,9 @@ int32_t AecmB200_GetDelayEstimate(AecmB200Batch *batch, int32_t first, int32_t c
 /* Multi-GPU group: nInstances split into contiguous shards (ceil-split), one batch per entry of devices[] (NULL =
  * devices 0..nDevices-1), driven from the calling thread.  Instances are independent, so shards never exchange
  * data: a group call submits every shard's slice of the host planes asynchronously, then waits for all of them.
- * first/count in the args address the group's global instance numbering; farendMask is not supported here. */
+ * first/count in the args address the group's global instance numbering; farendMask and instanceIndex are not supported
+ * here (both are laid out over the whole range).  Everything else -- InitEchoPath, the delay-estimator options, device
+ * planes -- goes through the shard's own batch handle (AecmB200_GroupShard). */
 typedef struct AecmB200Group AecmB200Group;
 AecmB200Group *AecmB200_GroupCreate(int32_t nInstances, int32_t nDevices, const int32_t *devices);
 void AecmB200_GroupFree(AecmB200Group *group);
