@@ -67,6 +67,7 @@ def parse_args():
     ap.add_argument("--no-parity", action="store_true")
     ap.add_argument("--realtime-seconds", type=float, default=10.0)
     ap.add_argument("--parity-sample", type=int, default=64, help="instances replayed on the CPU reference (whole job)")
+    ap.add_argument("--clock-sampler", default="nvml", choices=["nvml", "smi"], help="NVML thread (1 ms) or nvidia-smi -lms 20")
     ap.add_argument("--group", action="store_true", help="one process, all GPUs through AecmB200_Group* (e2e only)")
     ap.add_argument("--group-threads", type=int, default=0, help="--group: 1 = one submitting host thread per shard")
     return ap.parse_args()
@@ -316,7 +317,7 @@ def run_ours(args):
         host_ranks = [None] * world
         dist.all_gather_object(host_ranks, numa)
 
-    sampler = NvmlSampler(local)
+    sampler = NvmlSampler(local) if args.clock_sampler == "nvml" else ClockSampler(local)
     sampler.start()  # (the nvidia-smi fall-back takes about a second before its first sample: start early)
     batch = AecmBatch(B, local)
     stream = torch.cuda.current_stream(dev)
