@@ -30,7 +30,8 @@ __device__ __forceinline__ void mbar_init(uint64_t *bar) {
 }
 // Issues the two bulk loads of the record (lane 0) and waits for part A; part B is waited for where it is first used.
 __device__ __forceinline__ void bulk_load_record(AecmInstanceState *dst_smem, const AecmInstanceState *src_gmem, uint32_t bytes,
-                                                 uint64_t *bar_a, uint64_t *bar_b, uint32_t parity, int lane) {
+                                                 uint64_t *bar_a, uint64_t *bar_b, uint32_t parity, int lane,
+                                                 bool cta_sync_before_wait = false) {
     if (lane == 0) {
         const uint32_t a = smem_u32(bar_a), b = smem_u32(bar_b);
         const uint32_t bytes_b = bytes - AECM_STATE_PART_A;
@@ -46,6 +47,7 @@ __device__ __forceinline__ void bulk_load_record(AecmInstanceState *dst_smem, co
                      : "memory");
     }
     __syncwarp();
+    if (cta_sync_before_wait) __syncthreads();
     mbar_wait(bar_a, parity);
 }
 __device__ __forceinline__ void prefetch_line(const void *p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
@@ -111,10 +113,13 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, kCtasPerSm) aecm_call_kerne
         const int row = *my_row;
         if (row - warp >= a.count) break;  // the CTA's rows are exhausted (same trip count for all its warps)
         *my_row = row + stride;
-        if (kRowResync && row - warp != (int)blockIdx.x * kWarpsPerCta &&
-            (AECM_ROW_RESYNC == 1 || ((row - warp) / stride) % AECM_ROW_RESYNC == 0))
-            __syncthreads();  // (AECM_ROW_RESYNC = k > 1: only before every k-th row; measured)
+        // the CTA's rendezvous of this row (AECM_ROW_RESYNC = k > 1: only before every k-th row; measured).
+        // With AECM_LOAD_BEFORE_SYNC (default) the row's bulk loads are issued first: their latency runs behind the wait.
+        const bool need_sync = kRowResync && row - warp != (int)blockIdx.x * kWarpsPerCta &&
+                               (AECM_ROW_RESYNC == 1 || ((row - warp) / stride) % AECM_ROW_RESYNC == 0);
+        if (need_sync && !kLoadBeforeSync) __syncthreads();
         if (row >= a.count) {  // no row left for this warp in the CTA's last pass: keep the CTA's rendezvous count
+            if (need_sync && kLoadBeforeSync) __syncthreads();
             if (a.near_noisy)
                 for (int call = 0; call < a.n_calls; call++) idle_call(a.samples_per_call / AECM_FRAME_LEN);
             continue;
@@ -127,6 +132,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, kCtasPerSm) aecm_call_kerne
             inst = __ldg(&a.index[row]);
             if ((unsigned)inst >= (unsigned)planes.n_instances) {
                 if (a.status) a.status[row] = AECM_BAD_PARAMETER_ERROR;  // (every lane, same word: rare path, no lane test to keep)
+                if (need_sync && kLoadBeforeSync) __syncthreads();
                 if (a.near_noisy)
                     for (int call = 0; call < a.n_calls; call++) idle_call(a.samples_per_call / AECM_FRAME_LEN);
                 continue;
@@ -146,7 +152,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, kCtasPerSm) aecm_call_kerne
         }
         if (lane == 0) sc->stored_dirty = 0;
         const uint32_t phase = sc->phase;
-        bulk_load_record(st, g_state, rec_bytes, &sc->mbar_a, &sc->mbar_b, phase, lane);
+        bulk_load_record(st, g_state, rec_bytes, &sc->mbar_a, &sc->mbar_b, phase, lane, need_sync && kLoadBeforeSync);
         // ... and the stretch of the far-end jitter ring this call will read back (echo_control_mobile.cc:369-380:
         // up to 160 samples from the read cursor, which EstBufDelay may first move by one frame either way)
         if (lane < 6) {
