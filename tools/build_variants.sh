@@ -5,7 +5,6 @@
 #   v8_resync2.so  rendezvous only before every 2nd row (-DAECM_ROW_RESYNC=2)
 #   v8_syncframe/_syncblock.so  additional rendezvous before every frame / every potential block (-DAECM_SYNC_POINTS=1 / 2)
 #   v8_cta14.so    two 14-warp CTAs per SM instead of one 28-warp CTA (-DAECM_WARPS_PER_CTA=14)
-#   v8_loadafter.so  the row's bulk loads are issued after the CTA rendezvous instead of before it (-DAECM_LOAD_BEFORE_SYNC=0)
 #   v8_nobin64.so  MEASUREMENT ONLY, wrong output: the one-live-lane pass for bin 64 compiled out (-DAECM_BIN_PASSES=2)
 set -e
 ROOT=$(cd "$(dirname "$0")/.." && pwd)
@@ -23,7 +22,6 @@ rm -rf "$TMP"; TMP=$(mktemp -d)
 build v8_free "$TMP" "-DAECM_ROW_RESYNC=0"
 build v8_cta14 "$TMP" "-DAECM_WARPS_PER_CTA=14"
 build v8_resync2 "$TMP" "-DAECM_ROW_RESYNC=2"
-build v8_loadafter "$TMP" "-DAECM_LOAD_BEFORE_SYNC=0"
 build v8_syncframe "$TMP" "-DAECM_SYNC_POINTS=1"
 build v8_syncblock "$TMP" "-DAECM_SYNC_POINTS=2"
 build v8_nobin64 "$TMP" "-DAECM_BIN_PASSES=2"

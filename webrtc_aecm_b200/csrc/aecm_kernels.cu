@@ -28,10 +28,10 @@ __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)_
 __device__ __forceinline__ void mbar_init(uint64_t *bar) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(bar)));
 }
-// Issues the two bulk loads of the record (lane 0) and waits for part A; part B is waited for where it is first used.
-__device__ __forceinline__ void bulk_load_record(AecmInstanceState *dst_smem, const AecmInstanceState *src_gmem, uint32_t bytes,
-                                                 uint64_t *bar_a, uint64_t *bar_b, uint32_t parity, int lane,
-                                                 bool cta_sync_before_wait = false) {
+// Issues the two bulk loads of the record (lane 0).  Part A is waited for after the row's CTA rendezvous, part B where it
+// is first used.
+__device__ __forceinline__ void bulk_issue_record(AecmInstanceState *dst_smem, const AecmInstanceState *src_gmem, uint32_t bytes,
+                                                  uint64_t *bar_a, uint64_t *bar_b, int lane) {
     if (lane == 0) {
         const uint32_t a = smem_u32(bar_a), b = smem_u32(bar_b);
         const uint32_t bytes_b = bytes - AECM_STATE_PART_A;
@@ -47,8 +47,6 @@ __device__ __forceinline__ void bulk_load_record(AecmInstanceState *dst_smem, co
                      : "memory");
     }
     __syncwarp();
-    if (cta_sync_before_wait) __syncthreads();
-    mbar_wait(bar_a, parity);
 }
 __device__ __forceinline__ void prefetch_line(const void *p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
 __device__ __forceinline__ void prefetch_line_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
@@ -113,46 +111,43 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, kCtasPerSm) aecm_call_kerne
         const int row = *my_row;
         if (row - warp >= a.count) break;  // the CTA's rows are exhausted (same trip count for all its warps)
         *my_row = row + stride;
-        // the CTA's rendezvous of this row (AECM_ROW_RESYNC = k > 1: only before every k-th row; measured).
-        // With AECM_LOAD_BEFORE_SYNC (default) the row's bulk loads are issued first: their latency runs behind the wait.
-        const bool need_sync = kRowResync && row - warp != (int)blockIdx.x * kWarpsPerCta &&
-                               (AECM_ROW_RESYNC == 1 || ((row - warp) / stride) % AECM_ROW_RESYNC == 0);
-        if (need_sync && !kLoadBeforeSync) __syncthreads();
-        if (row >= a.count) {  // no row left for this warp in the CTA's last pass: keep the CTA's rendezvous count
-            if (need_sync && kLoadBeforeSync) __syncthreads();
-            if (a.near_noisy)
-                for (int call = 0; call < a.n_calls; call++) idle_call(a.samples_per_call / AECM_FRAME_LEN);
-            continue;
-        }
         // (derived from the volatile row word on purpose: otherwise the compiler hoists the per-lane prefetch offsets and
         // predicates out of the row loop and, with no register to keep them in, spills them to local memory)
         const int row_bytes = (a.samples_per_call + (row < 0 ? 1 : 0)) * (int)sizeof(int16_t);
-        int inst = a.first + row;
-        if (a.index) {  // scattered rows (combined scalar calls): the row names its instance
+        // which instance?  -1: this warp has no row in the CTA's last pass; -2: the row names an instance that does not exist
+        int inst = row < a.count ? a.first + row : -1;
+        if (inst >= 0 && a.index) {  // scattered rows (combined scalar calls): the row names its instance
             inst = __ldg(&a.index[row]);
-            if ((unsigned)inst >= (unsigned)planes.n_instances) {
-                if (a.status) a.status[row] = AECM_BAD_PARAMETER_ERROR;  // (every lane, same word: rare path, no lane test to keep)
-                if (need_sync && kLoadBeforeSync) __syncthreads();
-                if (a.near_noisy)
-                    for (int call = 0; call < a.n_calls; call++) idle_call(a.samples_per_call / AECM_FRAME_LEN);
-                continue;
-            }
+            if ((unsigned)inst >= (unsigned)planes.n_instances) inst = -2;
         }
-        const AecmInstanceState *g_state = planes.state + inst;
-        const int64_t off = (int64_t)row * a.row_stride;
-        {
+        if (inst >= 0) {
             // The audio rows of the first call are needed right after the record: start them on their way from HBM now,
             // one 128-byte line per lane, so that their latency overlaps the record copy instead of following it.
+            const int64_t off = (int64_t)row * a.row_stride;
             const int at = min(lane * 128, row_bytes - 1);  // lane 0.. cover the row, the last one its final byte
             if (lane * 128 < row_bytes + 128) {
                 if (a.far) prefetch_line(reinterpret_cast<const char *>(a.far + off) + at);
                 if (a.near_noisy) prefetch_line(reinterpret_cast<const char *>(a.near_noisy + off) + at);
                 if (use_clean) prefetch_line(reinterpret_cast<const char *>(a.near_clean + off) + at);
             }
+            if (lane == 0) sc->stored_dirty = 0;
+            // the record's bulk loads go out BEFORE the rendezvous: their latency runs behind the wait for the slowest warp
+            // (+0.3 ... +0.9 %, profiles/r02_variants_session12.txt)
+            bulk_issue_record(st, planes.state + inst, rec_bytes, &sc->mbar_a, &sc->mbar_b, lane);
         }
-        if (lane == 0) sc->stored_dirty = 0;
+        // The CTA's rendezvous of this row: ONE call site that every warp of the CTA passes once per row, with or without
+        // a row of its own (AECM_ROW_RESYNC = k > 1: only before every k-th row; measured).
+        if (kRowResync && row - warp != (int)blockIdx.x * kWarpsPerCta &&
+            (AECM_ROW_RESYNC == 1 || ((row - warp) / stride) % AECM_ROW_RESYNC == 0))
+            __syncthreads();
+        if (inst < 0) {
+            if (inst == -2 && a.status) a.status[row] = AECM_BAD_PARAMETER_ERROR;  // (every lane, same word: rare path)
+            if (a.near_noisy)  // keep the CTA's count of the finer rendezvous points (AECM_SYNC_POINTS experiments)
+                for (int call = 0; call < a.n_calls; call++) idle_call(a.samples_per_call / AECM_FRAME_LEN);
+            continue;
+        }
         const uint32_t phase = sc->phase;
-        bulk_load_record(st, g_state, rec_bytes, &sc->mbar_a, &sc->mbar_b, phase, lane, need_sync && kLoadBeforeSync);
+        mbar_wait(&sc->mbar_a, phase);
         // ... and the stretch of the far-end jitter ring this call will read back (echo_control_mobile.cc:369-380:
         // up to 160 samples from the read cursor, which EstBufDelay may first move by one frame either way)
         if (lane < 6) {

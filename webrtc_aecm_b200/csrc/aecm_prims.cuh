@@ -32,12 +32,6 @@ constexpr int kCtasPerSm = kWarpsPerCta >= 28 ? 1 : 28 / kWarpsPerCta;
 #define AECM_ROW_RESYNC 1
 #endif
 constexpr bool kRowResync = AECM_ROW_RESYNC != 0;
-// 1: a row's bulk loads are issued BEFORE the CTA rendezvous of that row, so their latency runs behind the wait for the
-// slowest warp (+0.3 % at 262 144 instances, +0.9 % at 32 768, profiles/r02_variants_session12.txt); 0: after it.
-#ifndef AECM_LOAD_BEFORE_SYNC
-#define AECM_LOAD_BEFORE_SYNC 1
-#endif
-constexpr bool kLoadBeforeSync = AECM_LOAD_BEFORE_SYNC != 0;
 // Finer rendezvous points inside a row: 1 = also before every 80-sample frame, 2 = also before every (potential) 64-sample
 // block.  Every warp of the CTA executes the same number of them per call whatever its instance is doing (start-up,
 // un-initialised, no row at all): see cta_rendezvous_* in aecm_frame_api.cuh.  Measured, DESIGN.md 4.1.
