@@ -285,6 +285,10 @@ __device__ __forceinline__ int api_process(const Ctx &c, const int16_t *near_noi
             return ret;
         }
     }
+    // aecm->msInSndCardBuf = msInSndCardBuf + 10 (:280): kept in the record from here on, not in a register across the frames
+    __syncwarp();
+    if (lane == 0) S.ms_in_snd_card_buf = ms;
+    __syncwarp();
     for (int i = 0; i < n_frames; i++) {  // :358-397
         cta_rendezvous_frame();
         int far_idx = -2;  // "replay farend_old" (even, so that the word-wide mover still applies)
@@ -299,10 +303,9 @@ __device__ __forceinline__ int api_process(const Ctx &c, const int16_t *near_noi
                 far_idx = d.far_rd;
                 fifo_move(d.far_rd, d.far_cnt, AECM_FAR_RING, AECM_FRAME_LEN);
             }
-            if ((i == 0 && fs == 8000) || (i == 1 && fs == 16000)) est_buf_delay(d, ms, S.mult);
+            if ((i == 0 && fs == 8000) || (i == 1 && fs == 16000)) est_buf_delay(d, S.ms_in_snd_card_buf, S.mult);
             __syncwarp();
             if (lane == 0) {
-                S.ms_in_snd_card_buf = ms;
                 S.far_rd = d.far_rd; S.far_cnt = d.far_cnt;
                 S.filt_delay = d.filt_delay; S.wrapper_known_delay = d.known_delay;
                 S.last_delay_diff = d.last_delay_diff; S.time_for_delay_change = d.time_for_delay_change;

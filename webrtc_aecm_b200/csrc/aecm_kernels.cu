@@ -146,8 +146,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, kCtasPerSm) aecm_call_kerne
                 for (int call = 0; call < a.n_calls; call++) idle_call(a.samples_per_call / AECM_FRAME_LEN);
             continue;
         }
-        const uint32_t phase = sc->phase;
-        mbar_wait(&sc->mbar_a, phase);
+        mbar_wait(&sc->mbar_a, sc->phase);
         // ... and the stretch of the far-end jitter ring this call will read back (echo_control_mobile.cc:369-380:
         // up to 160 samples from the read cursor, which EstBufDelay may first move by one frame either way)
         if (lane < 6) {
@@ -169,7 +168,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, kCtasPerSm) aecm_call_kerne
                 }
             }
         }
-        if (use_clean) mbar_wait(&sc->mbar_b, phase);  // the clean-path tail is needed from the first frame on
+        if (use_clean) mbar_wait(&sc->mbar_b, sc->phase);  // the clean-path tail is needed from the first frame on
 
         Ctx c;
         c.st = st;
