@@ -217,4 +217,20 @@ DLY_CONFIGS = [
     dict(id="robust_lookahead4_softreset", dly=dict(robust=1, max_lookahead=4), soft_reset=(97, 3), instances=(5, 10)),
     dict(id="softreset_only", dly=None, soft_reset=(50, 7), instances=(6, 15)),
     dict(id="robust_softreset_back20", dly=dict(robust=1), soft_reset=(37, -20), instances=(8, 0)),
+    # 45 s of steady echo: the winning histogram bin runs into its cap of 3000 (delay_estimator.cc:120-122) after ~27-40 s
+    dict(id="robust_long_steady", dly=dict(robust=1, allowed_offset=1), soft_reset=None, instances=(1,),
+         inputs=dict(n=3, seconds=45, seed=4711, delay_ms=(20, 60, 100))),
 ]
+
+
+def dly_inputs(cfg):
+    """(fs, spc, far, near, ms, run_kwargs) of a DLY_CONFIGS entry: the delay-sweep case unless the entry brings its own."""
+    from webrtc_aecm_b200.synth import synth_streams
+
+    if "inputs" not in cfg:
+        case = CASE_BY_NAME["c5_delay_sweep_0_120ms"]
+        far, near, _, ms = make_inputs(case)
+        return case["fs"], case["spc"], far, near, ms, run_kwargs(case)
+    i = cfg["inputs"]
+    far, near = synth_streams(i["n"], i["seconds"] * 16000, 16000, seed=i["seed"], delay_ms=list(i["delay_ms"]))
+    return 16000, 160, far, near, None, dict(fs=16000, samples_per_call=160, cng_mode=1, echo_mode=3, skip_far_every=0, extra_far_every=0)

@@ -208,6 +208,19 @@ class OracleInstance:
     def state(self) -> OracleState:
         return OracleState.from_address(self.h)
 
+    def set_delay_estimator_options(self, robust=0, allowed_offset=0, max_lookahead=-1, lookahead=-1):
+        f = self.lib.oracle_aecm_set_delay_estimator_options
+        f.argtypes = [C.c_void_p] + [C.c_int] * 4
+        return f(self.h, robust, allowed_offset, max_lookahead, lookahead)
+
+    def delay_estimate(self):
+        """(WebRtc_last_delay, WebRtc_last_delay_quality) of the instance."""
+        q = self.lib.oracle_aecm_last_delay_quality
+        q.restype, q.argtypes = C.c_float, [C.c_void_p]
+        d = self.lib.oracle_aecm_last_delay
+        d.restype, d.argtypes = C.c_int32, [C.c_void_p]
+        return int(d(self.h)), float(q(self.h))
+
     def close(self):
         if self.h:
             self.lib.oracle_aecm_free(self.h)

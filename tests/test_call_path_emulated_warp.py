@@ -12,7 +12,7 @@ import numpy as np
 import pytest
 
 import oracle_lib as ol
-from cases import CASE_BY_NAME, CASES, DLY_CONFIGS, far_mask, make_inputs, run_kwargs
+from cases import CASE_BY_NAME, CASES, DLY_CONFIGS, dly_inputs, far_mask, make_inputs, run_kwargs
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "..", "webrtc_aecm_b200", "csrc")
@@ -131,12 +131,11 @@ def test_delay_estimator_options_on_emulated_warp(emu, cfg):
     """SURVEY 8-f4 on the device code (kExt instantiation: robust validation with its float histogram, near-end lookahead,
     soft resets), run on the emulated warp: output AND the delay estimate after every call equal the oracle's, which
     tests/test_oracle.py pins to the reference driven through its own setters."""
-    case = CASE_BY_NAME["c5_delay_sweep_0_120ms"]
-    far, near, clean, ms = make_inputs(case)
-    spc = case["spc"]
+    fs, spc, far, near, ms, kw = dly_inputs(cfg)
+    case = dict(CASE_BY_NAME["c5_delay_sweep_0_120ms"], fs=fs, spc=spc)
     calls = far.shape[1] // spc
     want, ret, _, trace = ol.run_streams(far, near, impl="oracle", ms=ms, dly=cfg["dly"], soft_reset=cfg["soft_reset"],
-                                         delay_trace=True, **run_kwargs(case))
+                                         delay_trace=True, **kw)
     for instance in cfg["instances"]:
         got_trace = np.zeros(calls, dtype=np.int32)
         out, acc, _ = emu_run(emu, case, far, near, None, ms, instance, dly=cfg["dly"], soft_reset=cfg["soft_reset"],

@@ -565,16 +565,15 @@ def test_delay_estimator_options_match_reference(cfg):
     setters (tests/golden/dly_streams.json), and that reference itself when oracle/_ref/libaecm_ref_shim.so travelled."""
     from webrtc_aecm_b200 import AecmBatch
 
-    case = CASE_BY_NAME["c5_delay_sweep_0_120ms"]
-    far, near, clean, ms = make_inputs(case)
+    from cases import dly_inputs
+
+    fs, spc, far, near, ms, kw = dly_inputs(cfg)
     n, total = far.shape
-    spc = case["spc"]
     calls = total // spc
-    want, ret, _, wtrace = ol.run_streams(far, near, impl="oracle", ms=ms, dly=cfg["dly"], soft_reset=cfg["soft_reset"], delay_trace=True,
-                                          **run_kwargs(case))
+    want, ret, _, wtrace = ol.run_streams(far, near, impl="oracle", ms=ms, dly=cfg["dly"], soft_reset=cfg["soft_reset"], delay_trace=True, **kw)
     b = AecmBatch(n, 0)
-    assert b.init(case["fs"]) == 0
-    rc, st = b.set_config(case["cng"], case["echo_mode"])
+    assert b.init(fs) == 0
+    rc, st = b.set_config(kw["cng_mode"], kw["echo_mode"])
     assert rc == 0 and not st.any()
     if cfg["dly"] is not None:
         rc, st = b.set_delay_estimator_options(**cfg["dly"])
@@ -600,9 +599,20 @@ def test_delay_estimator_options_match_reference(cfg):
     gold = DLY_GOLD[cfg["id"]]
     assert stream_checksum(out) == gold["sha256"] and stream_checksum(trace) == gold["delay_trace_sha256"]
     assert np.isfinite(q).all() and (q >= 0).all() and (q <= 1).all()
+    if every == 0:  # WebRtc_last_delay_quality (a float) of a few instances, from oracle instances stepped alongside
+        for inst in sorted({0, n // 2, n - 1}):
+            o = ol.OracleInstance(fs, kw["cng_mode"], kw["echo_mode"])
+            if cfg["dly"] is not None:
+                assert o.set_delay_estimator_options(**cfg["dly"]) == 0
+            msi = 40 if ms is None else int(np.resize(ms, n)[inst])
+            for c in range(calls):
+                o.buffer_farend(far[inst, c * spc:(c + 1) * spc])
+                o.process(near[inst, c * spc:(c + 1) * spc], None, msi)
+            od, oq = o.delay_estimate()
+            assert (od, oq) == (int(d[inst]), float(q[inst])), (inst, od, oq, d[inst], q[inst])
+            o.close()
     if ol.ref_shim_path():
-        rout, _, _, rtrace = ol.run_streams(far, near, impl="ref", ms=ms, dly=cfg["dly"], soft_reset=cfg["soft_reset"], delay_trace=True,
-                                            **run_kwargs(case))
+        rout, _, _, rtrace = ol.run_streams(far, near, impl="ref", ms=ms, dly=cfg["dly"], soft_reset=cfg["soft_reset"], delay_trace=True, **kw)
         np.testing.assert_array_equal(out, rout)
         np.testing.assert_array_equal(trace, rtrace)
     b.close()

@@ -9,7 +9,7 @@ import numpy as np
 import pytest
 
 import oracle_lib as ol
-from cases import CASE_BY_NAME, CASES, DLY_CONFIGS, make_inputs, run_kwargs
+from cases import CASE_BY_NAME, CASES, DLY_CONFIGS, dly_inputs, make_inputs, run_kwargs
 from webrtc_aecm_b200.shard import stream_checksum
 
 GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
@@ -237,16 +237,14 @@ def test_delay_estimator_options_oracle_equals_reference(cfg):
     of the reference driven through its own setters (tests/golden/dly_streams.json, written by tools/make_golden.py via
     oracle/ref_shim.cc) -- output and the delay estimate after every call -- and, where the shim library is present, the
     arrays themselves."""
-    case = CASE_BY_NAME["c5_delay_sweep_0_120ms"]
-    far, near, clean, ms = make_inputs(case)
-    out, ret, _, trace = ol.run_streams(far, near, impl="oracle", ms=ms, dly=cfg["dly"], soft_reset=cfg["soft_reset"], delay_trace=True,
-                                        **run_kwargs(case))
+    _, _, far, near, ms, kw = dly_inputs(cfg)
+    out, ret, _, trace = ol.run_streams(far, near, impl="oracle", ms=ms, dly=cfg["dly"], soft_reset=cfg["soft_reset"], delay_trace=True, **kw)
     gold = DLY_GOLD[cfg["id"]]
     assert stream_checksum(out) == gold["sha256"] and stream_checksum(trace) == gold["delay_trace_sha256"]
     assert [int(r) for r in ret] == gold["ret_or"]
     if ol.ref_shim_path():
         rout, rret, _, rtrace = ol.run_streams(far, near, impl="ref", ms=ms, dly=cfg["dly"], soft_reset=cfg["soft_reset"],
-                                               delay_trace=True, **run_kwargs(case))
+                                               delay_trace=True, **kw)
         np.testing.assert_array_equal(out, rout)
         np.testing.assert_array_equal(trace, rtrace)
         np.testing.assert_array_equal(ret, rret)
@@ -256,7 +254,7 @@ def test_delay_estimator_options_change_the_estimate():
     """The configurations are not vacuous: robust validation, lookahead and soft resets each move the output away from the
     default wiring on these inputs, and the setters refuse what the reference's refuse."""
     base = json.load(open(os.path.join(GOLD, "streams.json")))["cases"]["c5_delay_sweep_0_120ms"]["sha256"]
-    shas = {k: v["sha256"] for k, v in DLY_GOLD.items()}
+    shas = {k: v["sha256"] for k, v in DLY_GOLD.items() if k != "robust_long_steady"}  # (that one has its own inputs)
     assert shas["statistics_only"] == base  # collecting the statistics alone changes nothing (aecm_core.cc:225)
     assert len(set(shas.values())) == len(shas) and all(v != base for k, v in shas.items() if k != "statistics_only")
     lib = ol.oracle()
@@ -272,3 +270,43 @@ def test_delay_estimator_options_change_the_estimate():
     assert lib.oracle_aecm_soft_reset_delay_estimator(a, 3) == 1  # 1 -> 0 (clamped)
     assert lib.oracle_aecm_soft_reset_delay_estimator(a, -9) == -6  # 0 -> 6 (clamped to max_lookahead)
     lib.oracle_aecm_free(C.c_void_p(a))
+
+
+@pytest.mark.skipif(ol.ref_shim_path() is None, reason="oracle/_ref/libaecm_ref_shim.so not built (needs /root/reference)")
+@pytest.mark.parametrize("robust", [0, 1])
+def test_last_delay_quality_oracle_equals_reference(robust):
+    """WebRtc_last_delay / WebRtc_last_delay_quality (delay_estimator_wrapper.cc:498-512, delay_estimator.cc:666-688): a float that
+    is the histogram height under robust validation and a function of last_delay_probability otherwise.  The reference
+    instance is driven call by call through its own API (the shim library) next to the oracle; both numbers must be
+    identical after every 50th call."""
+    fs, spc, _, far, near, _, _ = (16000, 160) + dly_inputs(DLY_CONFIGS[1])[1:]
+    R = C.CDLL(ol.ref_shim_path())
+    R.WebRtcAecm_Create.restype = C.c_void_p
+    R.ref_shim_last_delay_quality.restype = C.c_float
+    for name in ("WebRtcAecm_Init", "WebRtcAecm_BufferFarend", "WebRtcAecm_Process", "WebRtcAecm_Free",
+                 "ref_shim_set_delay_estimator_options", "ref_shim_last_delay", "ref_shim_last_delay_quality"):
+        getattr(R, name).argtypes = None
+    inst = 9
+    h = C.c_void_p(R.WebRtcAecm_Create())
+    assert R.WebRtcAecm_Init(h, fs) == 0
+    assert R.ref_shim_set_delay_estimator_options(h, robust, 0, -1, -1) == 0
+    o = ol.OracleInstance(fs, 1, 3)
+    assert o.set_delay_estimator_options(robust=robust) == 0
+    out = np.zeros(spc, dtype=np.int16)
+    seen = set()
+    for c in range(far.shape[1] // spc):
+        f = np.ascontiguousarray(far[inst, c * spc:(c + 1) * spc])
+        x = np.ascontiguousarray(near[inst, c * spc:(c + 1) * spc])
+        assert R.WebRtcAecm_BufferFarend(h, f.ctypes.data_as(C.c_void_p), C.c_size_t(spc)) == 0
+        assert R.WebRtcAecm_Process(h, x.ctypes.data_as(C.c_void_p), None, out.ctypes.data_as(C.c_void_p), C.c_size_t(spc), C.c_int16(40)) == 0
+        o.buffer_farend(f)
+        rc, w = o.process(x, None, 40)
+        np.testing.assert_array_equal(out, w)
+        if c % 50 == 49:
+            d, q = o.delay_estimate()
+            assert d == R.ref_shim_last_delay(h)
+            assert q == R.ref_shim_last_delay_quality(h), (c, q)
+            seen.add(q)
+    assert len(seen) > 3  # the quality moves
+    R.WebRtcAecm_Free(h)
+    o.close()

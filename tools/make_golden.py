@@ -26,7 +26,7 @@ sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 import oracle_lib as ol  # noqa: E402
-from cases import CASE_BY_NAME, CASES, DLY_CONFIGS, fft_adversarial_vectors, make_inputs, run_kwargs  # noqa: E402
+from cases import CASE_BY_NAME, CASES, DLY_CONFIGS, dly_inputs, fft_adversarial_vectors, make_inputs, run_kwargs  # noqa: E402
 from webrtc_aecm_b200.shard import stream_checksum  # noqa: E402
 
 FULL_VECTOR_CASES = ("16k_80_sample_calls", "16k_full_scale_alternating")
@@ -105,17 +105,15 @@ def main():
         print(case["name"], streams[case["name"]]["sha256"][:16], sorted(set(ret.tolist())))
     # the delay estimator's optional machinery, driven on the reference through oracle/ref_shim.cc
     dly = {}
-    case = CASE_BY_NAME["c5_delay_sweep_0_120ms"]
-    far, near, clean, ms = make_inputs(case)
     for cfg in DLY_CONFIGS:
-        out, ret, _, trace = ol.run_streams(far, near, impl="ref", ms=ms, dly=cfg["dly"], soft_reset=cfg["soft_reset"], delay_trace=True,
-                                            **run_kwargs(case))
+        fs_, spc_, far, near, ms, kw = dly_inputs(cfg)
+        out, ret, _, trace = ol.run_streams(far, near, impl="ref", ms=ms, dly=cfg["dly"], soft_reset=cfg["soft_reset"], delay_trace=True, **kw)
         dly[cfg["id"]] = {"sha256": stream_checksum(out), "delay_trace_sha256": stream_checksum(trace), "ret_or": [int(r) for r in ret],
                           "distinct_delays": int(len(np.unique(trace)))}
         print("dly", cfg["id"], dly[cfg["id"]]["sha256"][:16], dly[cfg["id"]]["distinct_delays"])
     with open(os.path.join(ROOT, "tests", "golden", "dly_streams.json"), "w") as f:
         json.dump({"generator": "tools/make_golden.py", "source": "oracle/_ref/libaecm_ref_shim.so (unmodified reference + oracle/ref_shim.cc)",
-                   "inputs": "tests/cases.py c5_delay_sweep_0_120ms, configurations DLY_CONFIGS", "cases": dly}, f, indent=1, sort_keys=True)
+                   "inputs": "tests/cases.py DLY_CONFIGS on dly_inputs(cfg): the delay-sweep case, or the entry's own stream", "cases": dly}, f, indent=1, sort_keys=True)
     vectors.update(stage_vectors(C.CDLL(ol.ref_path())))
     gdir = os.path.join(ROOT, "tests", "golden")
     os.makedirs(gdir, exist_ok=True)

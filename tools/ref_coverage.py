@@ -46,8 +46,12 @@ WHY = [
     ("ring_buffer.c", 56, 106, "allocation failures and NULL-argument checks"),
     ("ring_buffer.c", 128, 128, "ReadBuffer without a data_ptr: every AECM caller passes one"),
     ("ring_buffer.c", 146, 227, "NULL-argument checks; reading more than is buffered (callers check availability first)"),
-    ("delay_estimator.cc", 0, 10 ** 6, "float histogram / robust validation / soft reset / lookahead: disabled or uncalled in AECM (SURVEY 8-f4)"),
-    ("delay_estimator_wrapper.cc", 0, 10 ** 6, "float spectrum entry points, soft reset, lookahead, allocation failures: uncalled in AECM"),
+    ("delay_estimator.cc", 0, 10 ** 6, "allocation failures / NULL checks / history-size mismatch returns, soft reset by 0; "
+                                       "WebRtc_binary_last_delay_quality is not called by the stream runner: it is pinned by "
+                                       "tests/test_oracle.py::test_last_delay_quality_oracle_equals_reference, which drives the reference call "
+                                       "by call, and on the product by AecmB200_GetDelayEstimate in tests/test_gpu_parity.py"),
+    ("delay_estimator_wrapper.cc", 0, 10 ** 6, "float spectrum entry points (AECM uses the fixed-point ones), WebRtc_set_history_size (AECM's "
+                                               "far history is a fixed 100 rows), getters, allocation failures and argument checks"),
     ("signal_processing_library.cc", 0, 10 ** 6, "helpers AECM never calls (other SPL functions kept in the file)"),
     ("complex_fft.c", 0, 10 ** 6, "mode-0 (low-accuracy) branches: AECM always passes mode 1; allocation-free error returns"),
     ("real_fft.c", 0, 10 ** 6, "order-out-of-range returns"),
@@ -86,6 +90,24 @@ def main():
             "    ol.run_streams(far, near, impl='ref', clean=clean, ms=ms, threads=1, **cases.run_kwargs(c))\n"
         ) % (ROOT, os.path.join(ROOT, "tests"), so, names)
         subprocess.run([sys.executable, "-c", code], check=True)
+        # the delay estimator's optional machinery, through the shim (oracle/ref_shim.cc includes the reference's
+        # echo_control_mobile.cc and calls the estimator's own setters); the other objects are shared, so their counters add up
+        if not sys.argv[1:]:
+            shim_o = os.path.join(d, "ref_shim.o")
+            subprocess.run(["g++", "-std=c++11", "-O0", "-g", "--coverage", "-fPIC", "-I", REF, "-I", os.path.join(REF, "aecm"), "-c",
+                            os.path.join(ROOT, "oracle", "ref_shim.cc"), "-o", shim_o], check=True, cwd=d)
+            shim_so = os.path.join(d, "libaecm_ref_shim_cov.so")
+            subprocess.run(["g++", "-shared", "--coverage", "-o", shim_so, shim_o] +
+                           [o for o in objs if not o.endswith("echo_control_mobile.cc.o")], check=True)
+            code = (
+                "import sys; sys.path.insert(0, %r); sys.path.insert(0, %r)\n"
+                "import cases, oracle_lib as ol\n"
+                "ol.REF_SHIM_SO = %r\n"
+                "for cfg in cases.DLY_CONFIGS:\n"
+                "    fs, spc, far, near, ms, kw = cases.dly_inputs(cfg)\n"
+                "    ol.run_streams(far, near, impl='ref', ms=ms, threads=1, dly=cfg['dly'], soft_reset=cfg['soft_reset'], delay_trace=True, **kw)\n"
+            ) % (ROOT, os.path.join(ROOT, "tests"), shim_so)
+            subprocess.run([sys.executable, "-c", code], check=True)
         report = []
         for f in SRC_CC + SRC_C:
             subprocess.run(["gcov", "-o", d, os.path.join(d, f + ".o")], cwd=d, capture_output=True, text=True)
@@ -106,7 +128,8 @@ def main():
             report.append((f, hit, miss, missed))
     out = ["# Reference lines executed by the parity cases", "",
            "Generated by `python tools/ref_coverage.py` (gcov on an -O0 build of the unmodified reference, all cases of",
-           "`tests/cases.py` through the oracle's runner).  \"never reached\" lists source lines of the reference by number;",
+           "`tests/cases.py` through the oracle's runner, plus the eight delay-estimator configurations `DLY_CONFIGS` -- robust",
+           "validation, lookahead, soft resets, SURVEY 8-f4 -- through `oracle/ref_shim.cc`).  \"never reached\" lists source lines of the reference by number;",
            "the annotations say why a line is dead for every caller or which case family would be needed.", ""]
     out.append("| file | executed | never reached | share |")
     out.append("|---|---|---|---|")
