@@ -39,7 +39,7 @@ constexpr bool kRowResync = AECM_ROW_RESYNC != 0;
 #define AECM_SYNC_POINTS 0
 #endif
 constexpr int kSyncPoints = kRowResync ? AECM_SYNC_POINTS : 0;
-// MEASUREMENT ONLY (tools/run_variants.sh): 2 drops the one-live-lane pass for bin 64 from every 65-bin loop.  The output
+// MEASUREMENT ONLY (tools/build_variants.sh): 2 drops the one-live-lane pass for bin 64 from every 65-bin loop.  The output
 // is then WRONG; the build exists to bound what removing that pass could buy.  The product is built with 3.
 #ifndef AECM_BIN_PASSES
 #define AECM_BIN_PASSES 3
