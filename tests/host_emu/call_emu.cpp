@@ -29,13 +29,13 @@ size_t emu_state_bytes(void) { return sizeof(AecmInstanceState); }
 // One instance, n_calls API calls of `spc` samples.  ms: per-call msInSndCardBuf [n_calls].  far_ops: per call how
 // many times BufferFarend runs before Process (0 = underrun, 1 = normal, 2 = overrun).  Returns the OR of all return
 // codes; *state_out (optional) receives the final record.
-// dly (optional): {use, robust, allowed_offset, max_lookahead, lookahead, soft_reset_every, soft_reset_shift}: with
+// spc_calls (optional): per-call frame sizes.  dly (optional): {use, robust, allowed_offset, max_lookahead, lookahead, soft_reset_every, soft_reset_shift}: with
 // use != 0 the kExt instantiation runs, the options are applied after Init/set_config as AecmB200_SetDelayEstimatorOptions
 // does, and the delay estimator is soft-reset before the calls with (call % every) == every - 1, the sign of the shift
 // alternating (the schedule of oracle/aecm_runner.inc).  delay_trace (optional) [n_calls]: last_delay after every call.
 int emu_run_stream(int fs, int cng_mode, int echo_mode, const int16_t *far, const int16_t *near_noisy, const int16_t *near_clean,
-                   int16_t *out, int n_calls, int spc, const int16_t *ms, const uint8_t *far_ops, void *state_out,
-                   long *barriers, const int32_t *dly, int32_t *delay_trace) {
+                   int16_t *out, int n_calls, int spc_all, const int16_t *ms, const uint8_t *far_ops, void *state_out,
+                   long *barriers, const int32_t *dly, int32_t *delay_trace, const int32_t *spc_calls) {
     Emu *e = new Emu();
     memset(e, 0, sizeof(*e));
     int acc = 0;
@@ -61,8 +61,9 @@ int emu_run_stream(int fs, int cng_mode, int echo_mode, const int16_t *far, cons
         c.inst = 0;
         c.ext = &e->ext;
         c.lane = lane;
-        for (int call = 0; call < n_calls; call++) {
-            const size_t o = (size_t)call * (size_t)spc;
+        size_t o = 0;  // spc_calls (optional): the frame size of every call (80 or 160), overriding spc
+        for (int call = 0; call < n_calls; o += (size_t)(spc_calls ? spc_calls[call] : spc_all), call++) {
+            const int spc = spc_calls ? spc_calls[call] : spc_all;
             int r = 0;
             if (ext && dly[5] > 0 && (call % dly[5]) == dly[5] - 1) {
                 soft_reset_delay_estimator(&e->st, &e->ext, ((call / dly[5]) & 1) ? -dly[6] : dly[6], lane);

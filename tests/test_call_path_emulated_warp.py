@@ -74,7 +74,7 @@ def emu_run(lib, case, far, near, clean, ms, instance, want_state=False, misalig
                              ms_calls.ctypes.data_as(C.c_void_p), ops.ctypes.data_as(C.c_void_p),
                              None if state is None else state.ctypes.data_as(C.c_void_p), C.byref(nbar),
                              None if dly_arr is None else dly_arr.ctypes.data_as(C.c_void_p),
-                             None if delay_trace is None else delay_trace.ctypes.data_as(C.c_void_p))
+                             None if delay_trace is None else delay_trace.ctypes.data_as(C.c_void_p), None)
     return out, acc, state
 
 
@@ -144,3 +144,29 @@ def test_delay_estimator_options_on_emulated_warp(emu, cfg):
         assert bad.size == 0, f"instance {instance}: first differing sample {bad[0]} (call {bad[0] // spc})"
         np.testing.assert_array_equal(got_trace, trace[instance])
         assert acc == 0 and ret[instance] == 0
+
+
+@pytest.mark.parametrize("seed,fs", [(s, f) for s, f in __import__("test_fuzz_api").SCRIPTS if s % 3 != 2][:14])
+def test_random_call_sequences_on_emulated_warp(emu, seed, fs):
+    """The randomised API scripts of tests/test_fuzz_api.py (mixed 80/160-sample calls, msInSndCardBuf jumps and clamps,
+    under- and overruns, clean plane or not, all echo modes) through the device code on the emulated warp: output and the OR
+    of the return codes equal the oracle's, which the same scripts pin to the reference."""
+    import test_fuzz_api as fz
+
+    s = fz.make_script(seed, 500, fs)
+    want, rcs = fz.run_oracle(s)
+    n_calls = len(s["n"])
+    out = np.zeros_like(s["near"])
+    ms16 = np.ascontiguousarray(s["ms"].astype(np.int16))
+    spc_calls = np.ascontiguousarray(s["n"].astype(np.int32))
+    ops = np.ascontiguousarray(s["far_ops"])
+    cl = np.ascontiguousarray(s["cln"]) if s["clean"].all() else None
+    far, near = np.ascontiguousarray(s["far"]), np.ascontiguousarray(s["near"])
+    nbar = C.c_long(0)
+    acc = emu.emu_run_stream(fs, s["cng"], s["echo_mode"], far.ctypes.data_as(C.c_void_p), near.ctypes.data_as(C.c_void_p),
+                             None if cl is None else cl.ctypes.data_as(C.c_void_p), out.ctypes.data_as(C.c_void_p), n_calls, 0,
+                             ms16.ctypes.data_as(C.c_void_p), ops.ctypes.data_as(C.c_void_p), None, C.byref(nbar), None, None,
+                             spc_calls.ctypes.data_as(C.c_void_p))
+    bad = np.nonzero(out != want)[0]
+    assert bad.size == 0, f"first differing sample {bad[0]}"
+    assert acc == int(np.bitwise_or.reduce(rcs))

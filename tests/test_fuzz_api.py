@@ -1,0 +1,124 @@
+"""Randomised API call sequences: what the fixed case matrix cannot enumerate.
+
+A script is a list of 10 ms calls; every call draws its frame size (80 or 160 samples -- the reference accepts either at
+either rate, echo_control_mobile.cc:209, 268), its msInSndCardBuf (mostly steady, sometimes jumping, sometimes out of
+range) and how often BufferFarend runs before Process (0 = underrun, 1, 2 = overrun); a script passes a clean plane on
+every call or on none.
+The oracle and the unmodified reference are stepped call by call through their own entry points; output samples and
+return codes must agree call for call.  The same scripts drive the device code on the emulated warp
+(test_call_path_emulated_warp.py) and the GPU (test_gpu_parity.py)."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+import oracle_lib as ol
+from webrtc_aecm_b200.synth import synth_streams
+
+
+def make_script(seed, n_calls, fs):
+    """-> dict(n[n_calls], ms[n_calls], far_ops[n_calls], clean[n_calls] (bool), far, near, cln: int16 streams)"""
+    rng = np.random.default_rng(seed)
+    mixed = rng.random() < 0.7
+    base_n = 160 if fs == 16000 else 80
+    n = np.where(rng.random(n_calls) < (0.35 if mixed else 0.0), 240 - base_n, base_n).astype(np.int32)
+    ms = np.full(n_calls, int(rng.integers(0, 200)), dtype=np.int32)
+    k = 0
+    while k < n_calls:  # piecewise constant with jumps, a few out-of-range values
+        k += int(rng.integers(20, 120))
+        if k < n_calls:
+            ms[k:] = int(rng.choice([0, 10, 40, 80, 120, 250, 500, -5, 600, int(rng.integers(0, 500))]))
+    ms = ms + (rng.random(n_calls) < 0.1) * rng.integers(-3, 4, n_calls)
+    far_ops = rng.choice([0, 1, 2], size=n_calls, p=[0.06, 0.88, 0.06]).astype(np.uint8)
+    if rng.random() < 0.3:  # a long underrun
+        a = int(rng.integers(0, n_calls - 30))
+        far_ops[a:a + int(rng.integers(5, 30))] = 0
+    # a clean plane on every call or on none: switching it on and off in mid-stream leaves the reference's clean-frame FIFO
+    # short, and WebRtcAecm_ProcessFrame then hands ProcessBlock stale ring-buffer bytes or an uninitialised stack array
+    # (aecm_core.cc:537-546 with ring_buffer.c:113-131) -- there is no defined behaviour to be bit-exact with
+    clean = np.full(n_calls, rng.random() < 0.35)
+    total = int(n.sum())
+    far, near = synth_streams(1, total, fs, seed=seed, delay_ms=int(rng.integers(0, 110)), kind="stress" if rng.random() < 0.3 else "echo")
+    cln = synth_streams(1, total, fs, seed=seed + 1, delay_ms=5)[1]
+    return dict(n=n, ms=ms.astype(np.int32), far_ops=far_ops, clean=clean, far=far[0], near=near[0], cln=cln[0], fs=fs,
+                cng=int(rng.integers(0, 2)), echo_mode=int(rng.integers(0, 5)))
+
+
+def run_oracle(s):
+    o = ol.OracleInstance(s["fs"], s["cng"], s["echo_mode"])
+    out = np.zeros_like(s["near"])
+    rcs = []
+    pos = 0
+    for c in range(len(s["n"])):
+        n = int(s["n"][c])
+        sl = slice(pos, pos + n)
+        r = 0
+        for _ in range(int(s["far_ops"][c])):
+            r |= o.buffer_farend(s["far"][sl])
+        rc, w = o.process(s["near"][sl], s["cln"][sl] if s["clean"][c] else None, int(s["ms"][c]))
+        out[sl] = w
+        rcs.append(r | rc)
+        pos += n
+    o.close()
+    return out, np.array(rcs)
+
+
+def run_reference(s):
+    R = C.CDLL(ol.ref_path())
+    R.WebRtcAecm_Create.restype = C.c_void_p
+
+    class Cfg(C.Structure):
+        _fields_ = [("cngMode", C.c_int16), ("echoMode", C.c_int16)]
+
+    h = C.c_void_p(R.WebRtcAecm_Create())
+    assert R.WebRtcAecm_Init(h, s["fs"]) == 0
+    assert R.WebRtcAecm_set_config(h, Cfg(s["cng"], s["echo_mode"])) == 0
+    out = np.zeros_like(s["near"])
+    rcs = []
+    pos = 0
+    vp = lambda a: a.ctypes.data_as(C.c_void_p)
+    for c in range(len(s["n"])):
+        n = int(s["n"][c])
+        f = np.ascontiguousarray(s["far"][pos:pos + n])
+        x = np.ascontiguousarray(s["near"][pos:pos + n])
+        cl = np.ascontiguousarray(s["cln"][pos:pos + n]) if s["clean"][c] else None
+        o = np.zeros(n, dtype=np.int16)
+        r = 0
+        for _ in range(int(s["far_ops"][c])):
+            r |= R.WebRtcAecm_BufferFarend(h, vp(f), C.c_size_t(n))
+        r |= R.WebRtcAecm_Process(h, vp(x), None if cl is None else vp(cl), vp(o), C.c_size_t(n), C.c_int16(int(s["ms"][c])))
+        out[pos:pos + n] = o
+        rcs.append(r)
+        pos += n
+    R.WebRtcAecm_Free(h)
+    return out, np.array(rcs)
+
+
+SCRIPTS = [(seed, 8000 if seed % 3 == 0 else 16000) for seed in range(1, 41)]
+
+
+@pytest.mark.skipif(ol.ref_path() is None, reason="oracle/_ref/libaecm_ref.so not built (needs /root/reference)")
+@pytest.mark.parametrize("seed,fs", SCRIPTS)
+def test_random_call_sequences_oracle_equals_reference(seed, fs):
+    s = make_script(seed, 500, fs)
+    a, ra = run_oracle(s)
+    b, rb = run_reference(s)
+    np.testing.assert_array_equal(ra, rb)
+    bad = np.nonzero(a != b)[0]
+    assert bad.size == 0, f"first differing sample {bad[0]}"
+
+
+def test_scripts_exercise_what_they_claim():
+    """Across the scripts: both frame sizes at both rates, under- and overruns, clamped ms, clean planes, all echo modes."""
+    seen = {"mixed": 0, "under": 0, "over": 0, "clamp": 0, "clean": 0}
+    modes = set()
+    for seed, fs in SCRIPTS:
+        s = make_script(seed, 500, fs)
+        seen["mixed"] += len(set(s["n"].tolist())) == 2
+        seen["under"] += (s["far_ops"] == 0).any()
+        seen["over"] += (s["far_ops"] == 2).any()
+        seen["clamp"] += ((s["ms"] < 0) | (s["ms"] > 500)).any()
+        seen["clean"] += s["clean"].any()
+        modes.add(s["echo_mode"])
+    assert all(v >= 5 for v in seen.values()), seen
+    assert modes == {0, 1, 2, 3, 4}

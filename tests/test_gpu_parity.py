@@ -699,3 +699,49 @@ def test_far_and_near_planes_that_touch_but_are_two_pinned_allocations():
     finally:
         for a in (far, near):
             rt.cudaHostUnregister(a.ctypes.data)
+
+
+@pytest.mark.parametrize("seed,fs", [(3, 8000), (4, 16000), (7, 16000), (10, 16000), (12, 8000), (17, 16000)])
+def test_random_call_sequences_match_oracle(seed, fs):
+    """The randomised API scripts of tests/test_fuzz_api.py on the GPU: 12 instances share a script's call structure (mixed
+    80/160-sample calls, BufferFarend 0/1/2 times per Process, clean plane or not, echo mode, CNG) and differ in audio and in
+    their per-call msInSndCardBuf; every call is its own launch through AecmB200_BufferFarend / AecmB200_Process.  Output and
+    per-call status equal the oracle's, which the same scripts pin to the reference."""
+    import test_fuzz_api as fz
+    from webrtc_aecm_b200 import AecmBatch
+
+    n_inst, n_calls = 12, 400
+    base = fz.make_script(seed, n_calls, fs)
+    total = int(base["n"].sum())
+    far, near = synth_streams(n_inst, total, fs, seed=seed * 31, delay_ms=(np.arange(n_inst) * 9) % 110)
+    cln = synth_streams(n_inst, total, fs, seed=seed * 31 + 1, delay_ms=5)[1]
+    ms = np.stack([fz.make_script(seed * 100 + i, n_calls, fs)["ms"] for i in range(n_inst)]).astype(np.int16)
+    use_clean = bool(base["clean"].all())
+    want = np.zeros_like(near)
+    want_rc = np.zeros((n_inst, n_calls), dtype=np.int64)
+    for i in range(n_inst):
+        s = dict(base, far=far[i], near=near[i], cln=cln[i], ms=ms[i].astype(np.int32))
+        want[i], want_rc[i] = fz.run_oracle(s)
+    b = AecmBatch(n_inst, 0)
+    assert b.init(fs) == 0
+    rc, st = b.set_config(base["cng"], base["echo_mode"])
+    assert rc == 0 and not st.any()
+    out = np.zeros_like(near)
+    pos = 0
+    for c in range(n_calls):
+        n = int(base["n"][c])
+        sl = slice(pos, pos + n)
+        acc = np.zeros(n_inst, dtype=np.int64)
+        for _ in range(int(base["far_ops"][c])):
+            rc, status = b.buffer_farend(np.ascontiguousarray(far[:, sl]))
+            assert rc == 0
+            acc |= status
+        rc, o, status = b.process(np.ascontiguousarray(near[:, sl]), np.ascontiguousarray(cln[:, sl]) if use_clean else None, ms=ms[:, c])
+        assert rc == 0
+        acc |= status
+        out[:, sl] = o
+        np.testing.assert_array_equal(acc, want_rc[:, c], err_msg=f"return codes of call {c}")
+        pos += n
+    bad = np.nonzero((out != want).any(axis=1))[0]
+    assert bad.size == 0, f"instances {bad[:8]} differ, first sample {np.argmax(out[bad[0]] != want[bad[0]])}"
+    b.close()
