@@ -64,7 +64,9 @@ int32_t AecmB200_GetEchoPath(AecmB200Batch *batch, int32_t instance, void *echo_
 typedef struct {
     const int16_t *farend;        /* [count][rowStride] plane or NULL */
     const int16_t *nearendNoisy;  /* [count][rowStride] plane or NULL */
-    const int16_t *nearendClean;  /* optional plane */
+    const int16_t *nearendClean;  /* optional plane.  Per instance: on every Process call of a stream or on none -- switching it
+                                     on and off in mid-stream leaves the reference reading stale / uninitialised memory
+                                     (aecm_core.cc:537-546 with ring_buffer.c:113-131), so no behaviour is defined for it */
     int16_t *out;                 /* [count][rowStride] plane (required with nearendNoisy) */
     int64_t rowStride;            /* samples between instance rows; >= nCalls * nrOfSamples */
     int32_t first, count;         /* instance range */

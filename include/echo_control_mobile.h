@@ -49,7 +49,8 @@ int32_t WebRtcAecm_Init(void *aecmInst, int32_t sampFreq);
 int32_t WebRtcAecm_BufferFarend(void *aecmInst, const int16_t *farend, size_t nrOfSamples);
 /* The error WebRtcAecm_BufferFarend would return for these arguments, without buffering. */
 int32_t WebRtcAecm_GetBufferFarendError(void *aecmInst, const int16_t *farend, size_t nrOfSamples);
-/* Processes 80 or 160 near-end samples; nearendClean may be NULL; out may alias the input.
+/* Processes 80 or 160 near-end samples; nearendClean may be NULL (then for every call of the stream, as with the
+ * reference: its clean-frame FIFO only keeps step with the noisy one that way); out may alias the input.
  * Returns 0, an error code, or AECM_BAD_PARAMETER_WARNING when msInSndCardBuf was clamped to [0, 500]. */
 int32_t WebRtcAecm_Process(void *aecmInst, const int16_t *nearendNoisy, const int16_t *nearendClean, int16_t *out,
                            size_t nrOfSamples, int16_t msInSndCardBuf);
