@@ -29,13 +29,15 @@ size_t emu_state_bytes(void) { return sizeof(AecmInstanceState); }
 // One instance, n_calls API calls of `spc` samples.  ms: per-call msInSndCardBuf [n_calls].  far_ops: per call how
 // many times BufferFarend runs before Process (0 = underrun, 1 = normal, 2 = overrun).  Returns the OR of all return
 // codes; *state_out (optional) receives the final record.
-// spc_calls (optional): per-call frame sizes.  dly (optional): {use, robust, allowed_offset, max_lookahead, lookahead, soft_reset_every, soft_reset_shift}: with
+// spc_calls (optional): per-call frame sizes.  events / event_rc / quality_trace (optional): see the loop below.
+// dly (optional): {use, robust, allowed_offset, max_lookahead, lookahead, soft_reset_every, soft_reset_shift}: with
 // use != 0 the kExt instantiation runs, the options are applied after Init/set_config as AecmB200_SetDelayEstimatorOptions
 // does, and the delay estimator is soft-reset before the calls with (call % every) == every - 1, the sign of the shift
 // alternating (the schedule of oracle/aecm_runner.inc).  delay_trace (optional) [n_calls]: last_delay after every call.
 int emu_run_stream(int fs, int cng_mode, int echo_mode, const int16_t *far, const int16_t *near_noisy, const int16_t *near_clean,
                    int16_t *out, int n_calls, int spc_all, const int16_t *ms, const uint8_t *far_ops, void *state_out,
-                   long *barriers, const int32_t *dly, int32_t *delay_trace, const int32_t *spc_calls) {
+                   long *barriers, const int32_t *dly, int32_t *delay_trace, const int32_t *spc_calls, const int32_t *events,
+                   int n_events, int32_t *event_rc, float *quality_trace) {
     Emu *e = new Emu();
     memset(e, 0, sizeof(*e));
     int acc = 0;
@@ -69,12 +71,23 @@ int emu_run_stream(int fs, int cng_mode, int echo_mode, const int16_t *far, cons
                 soft_reset_delay_estimator(&e->st, &e->ext, ((call / dly[5]) & 1) ? -dly[6] : dly[6], lane);
                 __syncwarp();
             }
+            // events (optional, sorted by call): {call, kind, a, b, c, d} applied BEFORE that call; kind 0 = set_delay_options(a, b, c, d),
+            // kind 1 = soft_reset_delay_estimator(a); event_rc[k] receives what the device function returned
+            for (int k = 0; k < n_events; k++) {
+                const int32_t *ev = events + 6 * k;
+                if (ev[0] != call) continue;
+                const int er = ev[1] == 0 ? set_delay_options(&e->st, &e->ext, ev[2], ev[3], ev[4], ev[5], lane)
+                                          : soft_reset_delay_estimator(&e->st, &e->ext, ev[2], lane);
+                if (lane == 0 && event_rc) event_rc[k] = er;
+                __syncwarp();
+            }
             for (int rep = 0; rep < (far_ops ? far_ops[call] : 1); rep++) r |= api_buffer_farend(c, far + o, spc);
             if (ext) r |= api_process<true>(c, near_noisy + o, near_clean ? near_clean + o : nullptr, out + o, spc, ms ? ms[call] : 40);
             else r |= api_process<false>(c, near_noisy + o, near_clean ? near_clean + o : nullptr, out + o, spc, ms ? ms[call] : 40);
             if (lane == 0) {
                 acc |= r;
                 if (delay_trace) delay_trace[call] = e->st.s.last_delay;
+                if (quality_trace) quality_trace[call] = last_delay_quality(&e->st, &e->ext);
             }
         }
     });

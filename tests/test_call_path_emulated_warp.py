@@ -13,6 +13,7 @@ import pytest
 
 import oracle_lib as ol
 from cases import CASE_BY_NAME, CASES, DLY_CONFIGS, dly_inputs, far_mask, make_inputs, run_kwargs
+from webrtc_aecm_b200.synth import synth_streams
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "..", "webrtc_aecm_b200", "csrc")
@@ -74,7 +75,7 @@ def emu_run(lib, case, far, near, clean, ms, instance, want_state=False, misalig
                              ms_calls.ctypes.data_as(C.c_void_p), ops.ctypes.data_as(C.c_void_p),
                              None if state is None else state.ctypes.data_as(C.c_void_p), C.byref(nbar),
                              None if dly_arr is None else dly_arr.ctypes.data_as(C.c_void_p),
-                             None if delay_trace is None else delay_trace.ctypes.data_as(C.c_void_p), None)
+                             None if delay_trace is None else delay_trace.ctypes.data_as(C.c_void_p), None, None, 0, None, None)
     return out, acc, state
 
 
@@ -166,7 +167,64 @@ def test_random_call_sequences_on_emulated_warp(emu, seed, fs):
     acc = emu.emu_run_stream(fs, s["cng"], s["echo_mode"], far.ctypes.data_as(C.c_void_p), near.ctypes.data_as(C.c_void_p),
                              None if cl is None else cl.ctypes.data_as(C.c_void_p), out.ctypes.data_as(C.c_void_p), n_calls, 0,
                              ms16.ctypes.data_as(C.c_void_p), ops.ctypes.data_as(C.c_void_p), None, C.byref(nbar), None, None,
-                             spc_calls.ctypes.data_as(C.c_void_p))
+                             spc_calls.ctypes.data_as(C.c_void_p), None, 0, None, None)
     bad = np.nonzero(out != want)[0]
     assert bad.size == 0, f"first differing sample {bad[0]}"
     assert acc == int(np.bitwise_or.reduce(rcs))
+
+
+@pytest.mark.parametrize("seed", range(200, 208))
+def test_random_delay_estimator_option_changes_on_emulated_warp(emu, seed):
+    """SURVEY 8-f4 device functions under random use: the estimator's setters, soft resets by random shifts and re-creations
+    with a new max_lookahead hit the device code (set_delay_options, soft_reset_delay_estimator, process_binary_spectrum<true>)
+    at random calls; output, every setter's return value, the delay estimate and its float quality after every call equal the
+    oracle's (which tests/test_fuzz_api.py pins to the reference under the same kind of fire)."""
+    rng = np.random.default_rng(seed)
+    fs, spc, calls = 16000, 160, 500
+    far, near = synth_streams(1, calls * spc, fs, seed=seed, delay_ms=int(rng.integers(0, 115)))
+    far, near = np.ascontiguousarray(far[0]), np.ascontiguousarray(near[0])
+    max_la = int(rng.integers(0, 9))
+    events = [(0, 0, int(rng.integers(0, 2)), int(rng.integers(0, 4)), max_la, -1)]
+    for c in range(1, calls):
+        u = rng.random()
+        if u < 0.02:
+            events.append((c, 0, int(rng.integers(0, 2)), int(rng.integers(0, 5)), -1, int(rng.integers(-1, max_la + 3))))
+        elif u < 0.035:
+            events.append((c, 1, int(rng.integers(-30, 31)), 0, 0, 0))
+        elif u < 0.04:
+            max_la = int(rng.integers(0, 12))
+            events.append((c, 0, int(rng.integers(0, 2)), 0, max_la, -1))
+    ev = np.ascontiguousarray(np.array(events, dtype=np.int32))
+    # the oracle, stepped call by call with the same events
+    o = ol.OracleInstance(fs, 1, 3)
+    soft = ol.oracle().oracle_aecm_soft_reset_delay_estimator
+    soft.argtypes = [C.c_void_p, C.c_int]
+    want = np.zeros_like(near)
+    want_rc = np.zeros(len(events), dtype=np.int32)
+    want_d, want_q = np.zeros(calls, dtype=np.int32), np.zeros(calls, dtype=np.float32)
+    k = 0
+    for c in range(calls):
+        while k < len(events) and events[k][0] == c:
+            e = events[k]
+            want_rc[k] = o.set_delay_estimator_options(e[2], e[3], e[4], e[5]) if e[1] == 0 else soft(o.h, e[2])
+            k += 1
+        o.buffer_farend(far[c * spc:(c + 1) * spc])
+        rc, w = o.process(near[c * spc:(c + 1) * spc], None, 40)
+        want[c * spc:(c + 1) * spc] = w
+        want_d[c], want_q[c] = o.delay_estimate()
+    o.close()
+    out = np.zeros_like(near)
+    got_rc = np.full(len(events), 99, dtype=np.int32)
+    got_d, got_q = np.zeros(calls, dtype=np.int32), np.zeros(calls, dtype=np.float32)
+    dly = np.array([1, 0, 0, -1, -1, 0, 0], dtype=np.int32)  # the kExt instantiation, nothing set up front
+    nbar = C.c_long(0)
+    vp = lambda a: a.ctypes.data_as(C.c_void_p)
+    acc = emu.emu_run_stream(fs, 1, 3, vp(far), vp(near), None, vp(out), calls, spc, None, None, None, C.byref(nbar), vp(dly),
+                             vp(got_d), None, vp(ev), len(events), vp(got_rc), vp(got_q))
+    assert acc == 0
+    np.testing.assert_array_equal(got_rc, want_rc)
+    bad = np.nonzero(out != want)[0]
+    assert bad.size == 0, f"first differing sample {bad[0]} (call {bad[0] // spc})"
+    np.testing.assert_array_equal(got_d, want_d)
+    np.testing.assert_array_equal(got_q, want_q)
+    assert len(events) >= 8

@@ -122,3 +122,59 @@ def test_scripts_exercise_what_they_claim():
         modes.add(s["echo_mode"])
     assert all(v >= 5 for v in seen.values()), seen
     assert modes == {0, 1, 2, 3, 4}
+
+
+@pytest.mark.skipif(ol.ref_shim_path() is None, reason="oracle/_ref/libaecm_ref_shim.so not built (needs /root/reference)")
+@pytest.mark.parametrize("seed", range(100, 112))
+def test_random_delay_estimator_option_changes_oracle_equals_reference(seed):
+    """SURVEY 8-f4 under fire: at random calls of a stream the estimator's knobs are turned -- robust validation on/off, allowed
+    offset, lookahead (within a max_lookahead chosen at the start), soft resets by random shifts, even a re-creation with a new
+    max_lookahead -- on the reference (through oracle/ref_shim.cc) and on the oracle alike.  Output, the delay estimate and its
+    float quality must agree after every call."""
+    rng = np.random.default_rng(seed)
+    fs, spc, calls = 16000, 160, 700
+    far, near = synth_streams(1, calls * spc, fs, seed=seed, delay_ms=int(rng.integers(0, 115)))
+    far, near = far[0], near[0]
+    R = C.CDLL(ol.ref_shim_path())
+    R.WebRtcAecm_Create.restype = C.c_void_p
+    R.ref_shim_last_delay_quality.restype = C.c_float
+    h = C.c_void_p(R.WebRtcAecm_Create())
+    assert R.WebRtcAecm_Init(h, fs) == 0
+    o = ol.OracleInstance(fs, 1, 3)
+    soft = ol.oracle().oracle_aecm_soft_reset_delay_estimator
+    soft.argtypes = [C.c_void_p, C.c_int]
+    max_la = int(rng.integers(0, 9))
+    first = dict(robust=int(rng.integers(0, 2)), allowed_offset=int(rng.integers(0, 4)), max_lookahead=max_la, lookahead=-1)
+    assert R.ref_shim_set_delay_estimator_options(h, first["robust"], first["allowed_offset"], max_la, -1) == 0
+    assert o.set_delay_estimator_options(**first) == 0
+    out = np.zeros(spc, dtype=np.int16)
+    vp = lambda a: a.ctypes.data_as(C.c_void_p)
+    events = 0
+    for c in range(calls):
+        u = rng.random()
+        if u < 0.02:  # turn the setters (a lookahead beyond max_lookahead must be refused by both, identically)
+            args = (int(rng.integers(0, 2)), int(rng.integers(0, 5)), -1, int(rng.integers(-1, max_la + 3)))
+            assert R.ref_shim_set_delay_estimator_options(h, *args) == o.set_delay_estimator_options(*args)
+            events += 1
+        elif u < 0.035:
+            shift = int(rng.integers(-30, 31))
+            assert R.ref_shim_soft_reset_delay_estimator(h, shift) == soft(o.h, shift)
+            events += 1
+        elif u < 0.04:  # a fresh estimator with another max_lookahead
+            max_la = int(rng.integers(0, 12))
+            args = (int(rng.integers(0, 2)), 0, max_la, -1)
+            assert R.ref_shim_set_delay_estimator_options(h, *args) == o.set_delay_estimator_options(*args) == 0
+            events += 1
+        f = np.ascontiguousarray(far[c * spc:(c + 1) * spc])
+        x = np.ascontiguousarray(near[c * spc:(c + 1) * spc])
+        assert R.WebRtcAecm_BufferFarend(h, vp(f), C.c_size_t(spc)) == 0
+        assert R.WebRtcAecm_Process(h, vp(x), None, vp(out), C.c_size_t(spc), C.c_int16(40)) == 0
+        o.buffer_farend(f)
+        rc, w = o.process(x, None, 40)
+        assert rc == 0
+        np.testing.assert_array_equal(out, w, err_msg=f"call {c}")
+        d, q = o.delay_estimate()
+        assert d == R.ref_shim_last_delay(h) and q == R.ref_shim_last_delay_quality(h), (c, d, q)
+    assert events >= 10
+    R.WebRtcAecm_Free(h)
+    o.close()
