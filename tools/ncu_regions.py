@@ -1,9 +1,10 @@
 #!/usr/bin/env python3
 """Executed warp-instructions per source *section* of the device code (aecm_kernels.cu and its .cuh files) (sections = '// ----' banner comments
 and function heads), from an ncu report captured with --import-source on.  Usage:
-    python tools/ncu_regions.py gpurun_out/prof.ncu-rep 20480"""
-import collections, csv, io, re, subprocess, sys
+    python tools/ncu_regions.py gpurun_out/prof.ncu-rep 20480 [dir with the sources of the captured build]"""
+import collections, csv, io, os, re, subprocess, sys
 rep, nblocks = sys.argv[1], float(sys.argv[2])
+src_dir = sys.argv[3] if len(sys.argv) > 3 else None  # the report carries line numbers: read the sources of the captured build
 out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--print-source", "cuda,sass", "--csv"], capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(out)))
 cur = None; hdr = None; per = {}
@@ -17,7 +18,7 @@ for r in rows:
 tot = sum(v for v, _ in per.values()); tots = sum(s for _, s in per.values()) or 1
 files = sorted({f for f, _ in per})
 for f in files:
-    try: src = open(f).read().splitlines()
+    try: src = open(os.path.join(src_dir, os.path.basename(f)) if src_dir else f).read().splitlines()
     except OSError: src = []
     marks = [(1, "(file head)")]
     for i, line in enumerate(src, 1):
