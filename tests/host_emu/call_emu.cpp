@@ -26,6 +26,15 @@ extern "C" {
 
 size_t emu_state_bytes(void) { return sizeof(AecmInstanceState); }
 
+// the scalar primitives of aecm_prims.cuh, one value at a time (known-answer tests against the reference's SPL functions)
+int emu_div_by_bin(int n, int d) { return div_by_bin(n, d); }
+int emu_sqrt_floor(int v) { return sqrt_floor(v); }
+int emu_norm_w32(int a) { return norm_w32(a); }
+int emu_norm_u32(unsigned a) { return norm_u32(a); }
+int emu_norm_w16(int a) { return norm_w16(a); }
+int emu_log_energy_q8(unsigned e, int q) { return log_energy_q8(e, q); }
+int emu_add_sat32(int a, int b) { return add_sat32(a, b); }
+
 // One instance, n_calls API calls of `spc` samples.  ms: per-call msInSndCardBuf [n_calls].  far_ops: per call how
 // many times BufferFarend runs before Process (0 = underrun, 1 = normal, 2 = overrun).  Returns the OR of all return
 // codes; *state_out (optional) receives the final record.

@@ -119,7 +119,7 @@ constexpr DivTable make_div_table() {
 __device__ const DivTable kDivTable = make_div_table();
 __device__ __forceinline__ int div_by_bin(int n, int d) {  // d = bin index + 1 in [1, 65]
     if (d == 1) return n;
-    const uint32_t a = (uint32_t)abs(n);
+    const uint32_t a = n < 0 ? 0u - (uint32_t)n : (uint32_t)n;  // |n| as unsigned, defined for INT_MIN as well (-> 2^31)
     const uint32_t q = __umulhi(a, __ldg(&kDivTable.mul[d])) >> __ldg(&kDivTable.shift[d]);
     return n < 0 ? -(int)q : (int)q;
 }
