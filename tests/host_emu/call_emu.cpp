@@ -20,6 +20,11 @@ struct Emu {
     int16_t far_ring[AECM_FAR_RING];
 };
 
+// the 65-entry channel estimate an InitEchoPath event imports (tests/test_fuzz_api.event_path is the same rule in numpy)
+void emu_event_path(int seed, int16_t *path) {
+    for (int i = 0; i < AECM_BINS; i++) path[i] = (int16_t)(((uint32_t)seed * 1103515245u + 12345u + (uint32_t)i * 7919u) & 0x3fffu);
+}
+
 }  // namespace
 
 extern "C" {
@@ -81,12 +86,31 @@ int emu_run_stream(int fs, int cng_mode, int echo_mode, const int16_t *far, cons
                 __syncwarp();
             }
             // events (optional, sorted by call): {call, kind, a, b, c, d} applied BEFORE that call; kind 0 = set_delay_options(a, b, c, d),
-            // kind 1 = soft_reset_delay_estimator(a); event_rc[k] receives what the device function returned
+            // kind 1 = soft_reset_delay_estimator(a), kind 2 = set_config(cngMode a, echoMode b), kind 3 = Init(fs a),
+            // kind 4 = InitEchoPath(emu_event_path(a)); event_rc[k] receives what the device function returned
             for (int k = 0; k < n_events; k++) {
                 const int32_t *ev = events + 6 * k;
                 if (ev[0] != call) continue;
-                const int er = ev[1] == 0 ? set_delay_options(&e->st, &e->ext, ev[2], ev[3], ev[4], ev[5], lane)
-                                          : soft_reset_delay_estimator(&e->st, &e->ext, ev[2], lane);
+                int er = 0;
+                if (ev[1] == 0) {
+                    er = set_delay_options(&e->st, &e->ext, ev[2], ev[3], ev[4], ev[5], lane);
+                } else if (ev[1] == 1) {
+                    er = soft_reset_delay_estimator(&e->st, &e->ext, ev[2], lane);
+                } else if (ev[1] == 2) {  // aecm_set_config_kernel (one thread per instance there)
+                    if (lane == 0) er = set_config_checked(e->st.s, ev[2], ev[3]);
+                } else if (ev[1] == 3) {  // AecmB200_Init: aecm_init_kernel + the memsets of the two HBM planes
+                    init_instance(&e->st, ev[2], lane);
+                    init_delay_ext(&e->ext, lane);
+                    __syncwarp();
+                    if (lane == 0) {
+                        memset(e->far_hist, 0, sizeof(e->far_hist));
+                        memset(e->far_ring, 0, sizeof(e->far_ring));
+                    }
+                } else if (ev[1] == 4) {  // aecm_init_echo_path_kernel with the path emu_event_path(seed) below
+                    int16_t path[AECM_BINS];
+                    emu_event_path(ev[2], path);
+                    init_echo_path_core(&e->st, path, lane);
+                }
                 if (lane == 0 && event_rc) event_rc[k] = er;
                 __syncwarp();
             }

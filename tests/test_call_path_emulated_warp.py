@@ -173,6 +173,35 @@ def test_random_call_sequences_on_emulated_warp(emu, seed, fs):
     assert acc == int(np.bitwise_or.reduce(rcs))
 
 
+@pytest.mark.parametrize("seed,fs", [(s, f) for s, f in __import__("test_fuzz_api").SCRIPTS if s % 2 == 0][:10])
+def test_random_control_calls_in_mid_stream_on_emulated_warp(emu, seed, fs):
+    """set_config (valid and refused), Init (same or other rate) and InitEchoPath at random points of the random scripts through
+    the device functions the control kernels run (set_config_checked, init_instance + init_delay_ext, init_echo_path_core):
+    return values, output and the OR of the return codes equal the oracle's, which test_fuzz_api.py pins to the reference."""
+    import test_fuzz_api as fz
+
+    s = fz.make_script(seed, 500, fs)
+    events = fz.make_control_events(seed, 500)
+    want_ev = []
+    want, rcs = fz.run_oracle(s, events, want_ev)
+    ev = np.ascontiguousarray(np.array([(c, k, a, b, 0, 0) for c, k, a, b in events], dtype=np.int32))
+    got_ev = np.full(len(events), 99, dtype=np.int32)
+    out = np.zeros_like(s["near"])
+    ms16 = np.ascontiguousarray(s["ms"].astype(np.int16))
+    spc_calls = np.ascontiguousarray(s["n"].astype(np.int32))
+    ops = np.ascontiguousarray(s["far_ops"])
+    cl = np.ascontiguousarray(s["cln"]) if s["clean"].all() else None
+    far, near = np.ascontiguousarray(s["far"]), np.ascontiguousarray(s["near"])
+    nbar = C.c_long(0)
+    vp = lambda a: a.ctypes.data_as(C.c_void_p)
+    acc = emu.emu_run_stream(fs, s["cng"], s["echo_mode"], vp(far), vp(near), None if cl is None else vp(cl), vp(out), len(s["n"]), 0,
+                             vp(ms16), vp(ops), None, C.byref(nbar), None, None, vp(spc_calls), vp(ev), len(events), vp(got_ev), None)
+    assert got_ev.tolist() == want_ev and len(events) >= 3
+    bad = np.nonzero(out != want)[0]
+    assert bad.size == 0, f"first differing sample {bad[0]}"
+    assert acc == int(np.bitwise_or.reduce(rcs))
+
+
 @pytest.mark.parametrize("seed", range(200, 208))
 def test_random_delay_estimator_option_changes_on_emulated_warp(emu, seed):
     """SURVEY 8-f4 device functions under random use: the estimator's setters, soft resets by random shifts and re-creations

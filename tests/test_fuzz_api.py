@@ -44,8 +44,36 @@ def make_script(seed, n_calls, fs):
                 cng=int(rng.integers(0, 2)), echo_mode=int(rng.integers(0, 5)))
 
 
-def run_oracle(s):
+def event_path(seed):
+    """The channel estimate an InitEchoPath event imports (tests/host_emu/call_emu.cpp emu_event_path is the same rule)."""
+    return ((seed * 1103515245 + 12345 + np.arange(65, dtype=np.int64) * 7919) & 0x3FFF).astype(np.int16)
+
+
+def make_control_events(seed, n_calls):
+    """Control calls between the 10 ms calls of a script -> sorted list of (call, kind, a, b), applied BEFORE that call:
+    kind 2 = WebRtcAecm_set_config(cngMode a, echoMode b) -- sometimes with values the reference refuses (:421-428),
+    kind 3 = WebRtcAecm_Init(fs a) in mid-stream (same or the other rate; the default config comes back, :183-188),
+    kind 4 = WebRtcAecm_InitEchoPath(event_path(a)) (:481-503).  (Kinds 0 and 1 are the delay-estimator events of the emulation.)"""
+    rng = np.random.default_rng(seed + 7_000_000)
+    ev = []
+    for c in range(1, n_calls):
+        u = rng.random()
+        if u < 0.012:
+            ev.append((c, 2, int(rng.choice([0, 1, 0, 1, 2, -1])), int(rng.choice([0, 1, 2, 3, 4, 3, 5, -1]))))
+        elif u < 0.016:
+            ev.append((c, 3, int(rng.choice([8000, 16000])), 0))
+        elif u < 0.024:
+            ev.append((c, 4, int(rng.integers(0, 1 << 20)), 0))
+    return ev
+
+
+def _events_at(events, c):
+    return [e for e in events if e[0] == c]
+
+
+def run_oracle(s, events=(), event_rc=None):
     o = ol.OracleInstance(s["fs"], s["cng"], s["echo_mode"])
+    L = o.lib
     out = np.zeros_like(s["near"])
     rcs = []
     pos = 0
@@ -53,6 +81,16 @@ def run_oracle(s):
         n = int(s["n"][c])
         sl = slice(pos, pos + n)
         r = 0
+        for _, kind, a, b in _events_at(events, c):
+            if kind == 2:
+                er = L.oracle_aecm_set_config(o.h, a, b)
+            elif kind == 3:
+                er = L.oracle_aecm_init(o.h, a)
+            else:
+                pth = event_path(a)
+                er = L.oracle_aecm_init_echo_path(o.h, pth.ctypes.data_as(C.c_void_p), 130)
+            if event_rc is not None:
+                event_rc.append(er)
         for _ in range(int(s["far_ops"][c])):
             r |= o.buffer_farend(s["far"][sl])
         rc, w = o.process(s["near"][sl], s["cln"][sl] if s["clean"][c] else None, int(s["ms"][c]))
@@ -63,7 +101,7 @@ def run_oracle(s):
     return out, np.array(rcs)
 
 
-def run_reference(s):
+def run_reference(s, events=(), event_rc=None):
     R = C.CDLL(ol.ref_path())
     R.WebRtcAecm_Create.restype = C.c_void_p
 
@@ -84,6 +122,16 @@ def run_reference(s):
         cl = np.ascontiguousarray(s["cln"][pos:pos + n]) if s["clean"][c] else None
         o = np.zeros(n, dtype=np.int16)
         r = 0
+        for _, kind, a, b in _events_at(events, c):
+            if kind == 2:
+                er = R.WebRtcAecm_set_config(h, Cfg(a, b))
+            elif kind == 3:
+                er = R.WebRtcAecm_Init(h, a)
+            else:
+                pth = event_path(a)
+                er = R.WebRtcAecm_InitEchoPath(h, vp(pth), C.c_size_t(130))
+            if event_rc is not None:
+                event_rc.append(er)
         for _ in range(int(s["far_ops"][c])):
             r |= R.WebRtcAecm_BufferFarend(h, vp(f), C.c_size_t(n))
         r |= R.WebRtcAecm_Process(h, vp(x), None if cl is None else vp(cl), vp(o), C.c_size_t(n), C.c_int16(int(s["ms"][c])))
@@ -106,6 +154,31 @@ def test_random_call_sequences_oracle_equals_reference(seed, fs):
     np.testing.assert_array_equal(ra, rb)
     bad = np.nonzero(a != b)[0]
     assert bad.size == 0, f"first differing sample {bad[0]}"
+
+
+@pytest.mark.skipif(ol.ref_path() is None, reason="oracle/_ref/libaecm_ref.so not built (needs /root/reference)")
+@pytest.mark.parametrize("seed,fs", [(s_, f_) for s_, f_ in SCRIPTS if s_ % 2 == 0])
+def test_random_control_calls_in_mid_stream_oracle_equals_reference(seed, fs):
+    """set_config (valid and refused), Init (same or other rate) and InitEchoPath at random points of the random scripts:
+    every control call's return value, every 10 ms call's return code and every output sample equal the reference's."""
+    s = make_script(seed, 500, fs)
+    ev = make_control_events(seed, 500)
+    ea, eb = [], []
+    a, ra = run_oracle(s, ev, ea)
+    b, rb = run_reference(s, ev, eb)
+    assert ea == eb and len(ea) == len(ev)
+    np.testing.assert_array_equal(ra, rb)
+    bad = np.nonzero(a != b)[0]
+    assert bad.size == 0, f"first differing sample {bad[0]}"
+
+
+def test_control_events_cover_their_kinds():
+    kinds, refused = set(), 0
+    for seed, _ in SCRIPTS:
+        for _, kind, a, b in make_control_events(seed, 500):
+            kinds.add(kind)
+            refused += kind == 2 and (a not in (0, 1) or not 0 <= b <= 4)
+    assert kinds == {2, 3, 4} and refused >= 10
 
 
 def test_scripts_exercise_what_they_claim():

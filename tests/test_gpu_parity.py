@@ -745,3 +745,76 @@ def test_random_call_sequences_match_oracle(seed, fs):
     bad = np.nonzero((out != want).any(axis=1))[0]
     assert bad.size == 0, f"instances {bad[:8]} differ, first sample {np.argmax(out[bad[0]] != want[bad[0]])}"
     b.close()
+
+
+@pytest.mark.parametrize("seed,fs", [(2, 16000), (6, 8000), (14, 16000), (22, 16000)])
+def test_random_control_calls_in_mid_stream_match_oracle(seed, fs):
+    """Control calls in the middle of running streams, on sub-ranges of a batch: AecmB200_SetConfig (valid and refused
+    values), AecmB200_Init (same or the other rate -- the range starts over while its neighbours keep running) and
+    AecmB200_InitEchoPath between the 10 ms calls of the randomised scripts.  Per-instance status of every control call,
+    status of every 10 ms call and all output equal the oracle's, stepped per instance with the events that hit it
+    (tests/test_fuzz_api.py pins the same kind of script to the reference)."""
+    import test_fuzz_api as fz
+    from webrtc_aecm_b200 import AecmBatch
+
+    n_inst, n_calls = 12, 400
+    base = fz.make_script(seed, n_calls, fs)
+    total = int(base["n"].sum())
+    far, near = synth_streams(n_inst, total, fs, seed=seed * 37, delay_ms=(np.arange(n_inst) * 7) % 110)
+    cln = synth_streams(n_inst, total, fs, seed=seed * 37 + 1, delay_ms=5)[1]
+    use_clean = bool(base["clean"].all())
+    rng = np.random.default_rng(seed + 9_000_000)
+    events = []  # (call, kind, a, b, first, count)
+    for c, kind, a, b in fz.make_control_events(seed, n_calls) + fz.make_control_events(seed + 1000, n_calls):
+        first = int(rng.integers(0, n_inst))
+        events.append((c, kind, a, b, first, 1 if kind == 4 else int(rng.integers(1, n_inst - first + 1))))
+    events.sort(key=lambda e: e[0])
+    assert {e[1] for e in events} == {2, 3, 4}
+    want = np.zeros_like(near)
+    want_rc = np.zeros((n_inst, n_calls), dtype=np.int64)
+    want_ev = []
+    for i in range(n_inst):
+        mine = [(c, kind, a, b) for c, kind, a, b, first, count in events if first <= i < first + count]
+        s = dict(base, far=far[i], near=near[i], cln=cln[i])
+        rcs = []
+        want[i], want_rc[i] = fz.run_oracle(s, mine, rcs)
+        want_ev.append(rcs)
+    b = AecmBatch(n_inst, 0)
+    assert b.init(fs) == 0
+    rc, st = b.set_config(base["cng"], base["echo_mode"])
+    assert rc == 0 and not st.any()
+    got_ev = [[] for _ in range(n_inst)]
+    out = np.zeros_like(near)
+    pos = k = 0
+    for c in range(n_calls):
+        while k < len(events) and events[k][0] == c:
+            _, kind, a, b_, first, count = events[k]
+            if kind == 2:
+                rc, st = b.set_config(a, b_, first=first, count=count)
+                assert rc == 0
+                st = st.tolist()
+            elif kind == 3:
+                st = [b.init(a, first=first, count=count)] * count
+            else:
+                st = [b.init_echo_path(first, fz.event_path(a))]
+            for j in range(count):
+                got_ev[first + j].append(st[j])
+            k += 1
+        n = int(base["n"][c])
+        sl = slice(pos, pos + n)
+        acc = np.zeros(n_inst, dtype=np.int64)
+        for _ in range(int(base["far_ops"][c])):
+            rc, status = b.buffer_farend(np.ascontiguousarray(far[:, sl]))
+            assert rc == 0
+            acc |= status
+        rc, o, status = b.process(np.ascontiguousarray(near[:, sl]), np.ascontiguousarray(cln[:, sl]) if use_clean else None,
+                                  ms=np.full(n_inst, int(base["ms"][c]), dtype=np.int16))
+        assert rc == 0
+        acc |= status
+        out[:, sl] = o
+        np.testing.assert_array_equal(acc, want_rc[:, c], err_msg=f"return codes of call {c}")
+        pos += n
+    assert got_ev == want_ev
+    bad = np.nonzero((out != want).any(axis=1))[0]
+    assert bad.size == 0, f"instances {bad[:8]} differ, first sample {np.argmax(out[bad[0]] != want[bad[0]])}"
+    b.close()

@@ -39,6 +39,18 @@ __device__ void apply_config(AecmScalars &S, int cng_mode, int echo_mode) {  // 
     S.sup_diff_bd = pb - pd;
 }
 
+// WebRtcAecm_set_config with its validation (echo_control_mobile.cc:410-430) on an initialised or uninitialised record
+__device__ __forceinline__ int set_config_checked(AecmScalars &S, int cng_mode, int echo_mode) {
+    if (S.init_flag != AECM_INIT_MAGIC) return AECM_UNINITIALIZED_ERROR;
+    if (cng_mode != 0 && cng_mode != 1) return AECM_BAD_PARAMETER_ERROR;
+    if (echo_mode < 0 || echo_mode > 4) {
+        S.cng_mode = cng_mode;  // the reference assigns cngMode before validating echoMode (:424-428)
+        return AECM_BAD_PARAMETER_ERROR;
+    }
+    apply_config(S, cng_mode, echo_mode);
+    return 0;
+}
+
 // ---- the delay estimator's optional machinery on the AecmDelayExt record (one warp per instance) ----
 // WebRtc_InitBinaryDelayEstimator's share of it (delay_estimator.cc:483-504): statistics and near history are cleared, the
 // properties of the estimator object (robust_validation_enabled, allowed_offset, lookahead, near_history_size) stay.

@@ -253,18 +253,7 @@ __global__ void aecm_set_config_kernel(AecmBatchPlanes planes, int first, int co
                                        int32_t *status) {
     const int row = blockIdx.x * blockDim.x + threadIdx.x;
     if (row >= count) return;
-    AecmScalars &S = planes.state[first + row].s;
-    int r = 0;
-    if (S.init_flag != AECM_INIT_MAGIC) {
-        r = AECM_UNINITIALIZED_ERROR;
-    } else if (cng_mode != 0 && cng_mode != 1) {
-        r = AECM_BAD_PARAMETER_ERROR;
-    } else if (echo_mode < 0 || echo_mode > 4) {
-        S.cng_mode = cng_mode;  // the reference assigns cngMode before validating echoMode (:424-428)
-        r = AECM_BAD_PARAMETER_ERROR;
-    } else {
-        apply_config(S, cng_mode, echo_mode);
-    }
+    const int r = set_config_checked(planes.state[first + row].s, cng_mode, echo_mode);
     if (status) status[row] = r;
 }
 
