@@ -93,9 +93,22 @@ struct Tw {
     int c, s;
 };
 
+// AECM_FMA_BIAS (bit 0: forward butterflies, bit 1: inverse butterflies): the butterflies are written as multiply-add
+// chains whose power-of-two factors the compiler cannot see (opaque()), so that it emits IMAD (fma pipe) where it would
+// otherwise strength-reduce to SHF / LOP3 / IADD3 (alu pipe).
+// Same values bit for bit (wrapping 32-bit arithmetic); only the pipe the work lands on changes: the kernel's mix is 50 %
+// alu-pipe against 25 % fma-pipe instructions and each pipe takes one warp-instruction every two cycles.
+#ifndef AECM_FMA_BIAS
+#define AECM_FMA_BIAS 0
+#endif
+__device__ __forceinline__ int opaque(int v) {
+    asm("" : "+r"(v));
+    return v;
+}
+
 // warp-uniform block-floating parameters of one inverse stage (complex_fft.c:381-396)
 struct InvScale {
-    int qs;     // 2^(16 - shift)
+    int qs;     // 2^(16 - shift)  (forward: 2^15, see fwd_scale)
     int mult;   // 2 for shift 0, else 1
     int d;      // 1 for shift 2, else 0
     int c_i;    // 2^15 + addi
@@ -110,6 +123,16 @@ __device__ __forceinline__ InvScale inv_scale(int peak) {
     s.d = s.shift == 2;
     s.addi = s.shift == 2 ? 0 : s.mult;
     s.c_i = 32768 + s.addi;
+#if AECM_FMA_BIAS & 2
+    s.qs = opaque(s.qs);
+    s.mult = opaque(s.mult);
+    s.c_i = opaque(s.c_i);
+#endif
+    return s;
+}
+__device__ __forceinline__ InvScale fwd_scale() {  // the forward transform only uses qs (as the opaque factor 2^15)
+    InvScale s{};
+    s.qs = (AECM_FMA_BIAS & 1) ? opaque(32768) : 32768;
     return s;
 }
 
@@ -118,7 +141,23 @@ __device__ __forceinline__ InvScale inv_scale(int peak) {
 template <bool kInv>
 __device__ __forceinline__ void butterfly(int qr, int qi, int xr, int xi, Tw w, const InvScale &sc, int &vir, int &vii,
                                           int &vjr, int &vji) {
-    if (!kInv) {
+    if (!kInv && (AECM_FMA_BIAS & 1)) {  // V_i = q*2^15 + 2^15 + 1 + P as a chain of three IMADs, V_j = (2 q*2^15 + 2^16 + 1) - V_i
+        const int br = qr * sc.qs + 32769, bi = qi * sc.qs + 32769;
+        const int cr = qr * sc.qs + 32768, ci = qi * sc.qs + 32768;
+        vir = (int)((uint32_t)(w.c * xr) + (uint32_t)opaque(w.s * xi + br));
+        vii = (int)((uint32_t)(w.c * xi) - (uint32_t)opaque(w.s * xr - bi));
+        vjr = (int)((uint32_t)br + (uint32_t)cr - (uint32_t)vir);
+        vji = (int)((uint32_t)bi + (uint32_t)ci - (uint32_t)vii);
+    } else if (kInv && (AECM_FMA_BIAS & 2)) {
+        const int P = (w.c * xr + sc.d - w.s * xi) >> sc.d;
+        const int Q = (w.c * xi + sc.d + w.s * xr) >> sc.d;
+        const int br = qr * sc.qs + sc.c_i, bi = qi * sc.qs + sc.c_i;
+        const int cr = qr * sc.qs + 32768, ci = qi * sc.qs + 32768;  // c_i - addi = 2^15 for every shift
+        vir = (int)((uint32_t)P * (uint32_t)sc.mult + (uint32_t)br);
+        vii = (int)((uint32_t)Q * (uint32_t)sc.mult + (uint32_t)bi);
+        vjr = (int)((uint32_t)br + (uint32_t)cr - (uint32_t)vir);
+        vji = (int)((uint32_t)bi + (uint32_t)ci - (uint32_t)vii);
+    } else if (!kInv) {
         const int P = w.c * xr + w.s * xi;
         const int Q = w.c * xi - w.s * xr;
         const int br = qr * 32768 + 32769, bi = qi * 32768 + 32769;
@@ -231,7 +270,7 @@ template <int NS>
 __device__ __forceinline__ void forward128(const int (&x)[NS][4], uint32_t *tile, const int2 *tw_tab, const LaneWords lw,
                                            int lane, int (&out_re)[NS][3], int (&out_im)[NS][3]) {
     Points<NS> z;
-    const InvScale none{};
+    const InvScale none = fwd_scale();
     // layout A: position 4L + r holds time index brev7(4L + r) = brev5(L) + 32 * {0, 2, 1, 3}[r]
 #pragma unroll
     for (int n = 0; n < NS; n++) {
