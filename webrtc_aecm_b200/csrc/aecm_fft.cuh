@@ -99,7 +99,7 @@ struct Tw {
 // Same values bit for bit (wrapping 32-bit arithmetic); only the pipe the work lands on changes: the kernel's mix is 50 %
 // alu-pipe against 25 % fma-pipe instructions and each pipe takes one warp-instruction every two cycles.
 #ifndef AECM_FMA_BIAS
-#define AECM_FMA_BIAS 0
+#define AECM_FMA_BIAS 2
 #endif
 __device__ __forceinline__ int opaque(int v) {
     asm("" : "+r"(v));
