@@ -1,9 +1,11 @@
 /*
- * fake_batch.c -- TEST INFRASTRUCTURE.  The subset of the batched ABI (include/aecm_b200.h) that the scalar-API layer
- * webrtc_aecm_b200/csrc/echo_control_mobile.c calls, implemented on the CPU oracle, so that the layer's host logic --
- * handle pools, the request combiner (leader election, rounds, hand-over), the deferred far end, pool teardown -- can run
- * under ThreadSanitizer on a machine without a GPU (tests/test_scalar_combiner_tsan.py).  Nothing here is shipped or
- * measured; the product's batch is csrc/aecm_batch.c on CUDA.
+ * fake_batch.c -- TEST INFRASTRUCTURE.  The subset of the batched ABI (include/aecm_b200.h) that the product's two host
+ * programs above the batch call -- the scalar-API layer csrc/echo_control_mobile.c and the WAV tool csrc/aecm_wav_batch.c --
+ * implemented on the CPU oracle, so that their host logic (handle pools, the request combiner with its leader election and
+ * hand-over, the deferred far end, pool teardown; reader/writer threads, sharding, lockstep chunks, the Submit/Wait
+ * pipeline) can run under ThreadSanitizer / AddressSanitizer on a machine without a GPU
+ * (tests/test_scalar_combiner_tsan.py, tests/test_wav_batch_on_stand_in.py).  Nothing here is shipped or measured; the
+ * product's batch is csrc/aecm_batch.c on CUDA.
  *
  * Semantics kept from the real batch: a call is applied to rows in lockstep; status[r] = first non-zero return code of
  * the row's calls; Submit on a busy slot is refused; Wait on an idle slot is a no-op.  Like the real batch, this one is
@@ -165,4 +167,9 @@ int32_t AecmB200_WaitStream(AecmB200Batch *b, int32_t slot) {
     b->busy[slot] = 0;
     leave(b);
     return 0;
+}
+
+const char *AecmB200_LastError(const AecmB200Batch *b) {
+    (void)b;
+    return "stand-in batch: no device errors";
 }

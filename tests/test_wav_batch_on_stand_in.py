@@ -1,0 +1,85 @@
+"""aecm_wav_batch's host logic on the CPU, under sanitizers.
+
+csrc/aecm_wav_batch.c (RIFF reader/writer, reader and writer threads, sharding over devices, lockstep chunks with instances
+dropping out as their files end, the pipelined Submit/Wait loop, per-pair failure handling) is compiled unchanged against
+tests/host_emu/fake_batch.c -- the CPU stand-in for the device batch, on the oracle -- once with AddressSanitizer +
+UBSan and once with ThreadSanitizer, and must write every <near>_out.wav byte-identical to the reference CLI's
+(oracle/_ref/aecm_run_ref: unmodified main.cc + reference library), the scenarios of tests/test_gpu_wav_batch.py.  The GPU
+suite runs the shipped binary over the real batch; this one is about the tool's own memory and thread safety."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from test_gpu_wav_batch import make_pairs, reference_outputs
+from test_wav_batch_io import REF_BIN, write_wav
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+
+pytestmark = pytest.mark.skipif(not os.path.exists(REF_BIN), reason="oracle/_ref/aecm_run_ref not built (needs /root/reference)")
+
+SAN = {"asan_ubsan": (["-fsanitize=address,undefined", "-fno-sanitize-recover=undefined"], "ERROR: AddressSanitizer", "runtime error:"),
+       "tsan": (["-fsanitize=thread"], "WARNING: ThreadSanitizer", "WARNING: ThreadSanitizer")}
+
+
+@pytest.fixture(scope="module", params=sorted(SAN))
+def tool(request, tmp_path_factory):
+    flags, *marks = SAN[request.param]
+    exe = str(tmp_path_factory.mktemp("wavtool") / f"aecm_wav_batch_{request.param}")
+    cmd = ["gcc", *flags, "-O1", "-g", "-std=gnu11", "-I", os.path.join(ROOT, "include"), "-I", os.path.join(ROOT, "webrtc_aecm_b200", "csrc"),
+           os.path.join(ROOT, "webrtc_aecm_b200", "csrc", "aecm_wav_batch.c"), os.path.join(HERE, "host_emu", "fake_batch.c"),
+           os.path.join(ROOT, "oracle", "aecm_oracle.c"), "-o", exe, "-lpthread", "-lm"]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0 and "san" in r.stderr.lower() and "cannot find" in r.stderr.lower():
+        pytest.skip("sanitizer runtime not available")
+    assert r.returncode == 0, r.stderr
+    return exe, marks
+
+
+def run(tool, *args):
+    exe, marks = tool
+    env = dict(os.environ, ASAN_OPTIONS="detect_leaks=1:abort_on_error=0", TSAN_OPTIONS="halt_on_error=0")
+    r = subprocess.run([exe, *map(str, args)], capture_output=True, text=True, timeout=900, env=env)
+    for m in marks:
+        assert m not in r.stderr, r.stderr[-4000:]
+    return r
+
+
+@pytest.mark.parametrize("extra", [[], ["--devices", "0,0,0", "--chunk-calls", "37"]], ids=["one_shard", "three_shards_odd_chunks"])
+def test_outputs_byte_identical_to_the_reference_cli(tool, tmp_path, extra):
+    pairs = make_pairs(tmp_path, 9, seed=31)
+    odd = tmp_path / "odd"  # an unsupported rate rides along: written back unchanged by both
+    odd.mkdir()
+    x = (np.arange(22050) * 13 % 5000 - 2500).astype(np.int16)
+    write_wav(odd / "far.wav", x, 22050)
+    write_wav(odd / "near.wav", x[::-1], 22050)
+    pairs.append(odd)
+    want = reference_outputs(pairs, tmp_path)
+    args = []
+    for d in pairs:
+        args += [d / "far.wav", d / "near.wav"]
+    res = run(tool, *extra, *args)
+    assert res.returncode == 0, res.stderr + res.stdout
+    for d in pairs:
+        assert open(d / "near_out.wav", "rb").read() == want[d.name], d.name
+    assert "10 pairs written" in res.stdout
+
+
+def test_one_unreadable_pair_costs_only_its_own_output(tool, tmp_path):
+    pairs = make_pairs(tmp_path, 4, seed=9)
+    want = reference_outputs(pairs, tmp_path)
+    (tmp_path / "junk_far.wav").write_bytes(b"this is not a RIFF file")
+    (tmp_path / "junk_near.wav").write_bytes(b"RIFF\x00\x00\x00\x00nope")
+    args = []
+    for d in pairs[:2]:
+        args += [d / "far.wav", d / "near.wav"]
+    args += [tmp_path / "junk_far.wav", tmp_path / "junk_near.wav"]
+    for d in pairs[2:]:
+        args += [d / "far.wav", d / "near.wav"]
+    res = run(tool, *args)
+    assert res.returncode == 1, (res.stdout, res.stderr)
+    assert "1 pair(s) unreadable" in res.stderr and "4 pairs written" in res.stdout
+    for d in pairs:
+        assert open(d / "near_out.wav", "rb").read() == want[d.name], d.name
