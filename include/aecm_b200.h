@@ -58,7 +58,9 @@ int32_t AecmB200_GetEchoPath(AecmB200Batch *batch, int32_t instance, void *echo_
  *          WebRtcAecm_Process(inst, nearendNoisy + r*rowStride + c*nrOfSamples,
  *                             nearendClean ? nearendClean + ... : NULL, out + ..., nrOfSamples,
  *                             msInSndCardBuf ? msInSndCardBuf[r] : msUniform);                        (:135-140)
- * status[r] receives the first non-zero return code among those calls (0 if none).
+ * status[r] receives the first non-zero return code among those calls (0 if none).  Where WebRtcAecm_Process refuses a call
+ * (an error code such as AECM_UNINITIALIZED_ERROR; not the AECM_BAD_PARAMETER_WARNING of a clamped msInSndCardBuf, which is
+ * returned after processing) the reference leaves `out` untouched; here the row's `out` samples of that call are unspecified.
  * nCalls > 1 fuses consecutive 10 ms calls into one launch with the instance state held on-chip.
  */
 typedef struct {

@@ -7,7 +7,8 @@ real runtime, and every kernel launch steps the CPU oracle.  The arithmetic is n
 planes, the four stream slots and their events, kernel order across slots, main-stream / slot-stream hand-over, index
 checks, status delivery, the group API, the scalar combiner -- under an execution order that a real GPU would only pick on a
 bad day.  A subset of the GPU suite's own tests runs against the model library (in a subprocess: the library is chosen at
-import), followed by cases that need the model's hooks (tests/host_emu/model_cases.py).  Two mutants of aecm_batch.c with a
+import), followed by cases that need the model's hooks (tests/host_emu/model_cases.py) and by model-based fuzzing of the
+batched ABI against the header's contract (tests/host_emu/model_fuzz.py).  Three mutants of aecm_batch.c with a
 dependency removed must FAIL: the model is not vacuous.
 
 TEST INFRASTRUCTURE: the model library is built into a temporary directory, announces itself on stderr when loaded, and is
@@ -36,8 +37,8 @@ def build(out_dir, batch_src=None, name="libaecm_b200_hostmodel.so", extra=()):
     return lib
 
 
-def run_pytest(lib, order, *args):
-    env = dict(os.environ, AECM_B200_LIB=lib, FAKE_CUDA_ORDER=order, FAKE_CUDA_DEVICES="2")
+def run_pytest(lib, order, *args, seeds=()):
+    env = dict(os.environ, AECM_B200_LIB=lib, FAKE_CUDA_ORDER=order, FAKE_CUDA_DEVICES="2", MODEL_FUZZ_SEEDS=",".join(map(str, seeds)) or "1,2,3,4,5")
     return subprocess.run([sys.executable, "-m", "pytest", "-q", "-x", "-p", "no:cacheprovider", *args], capture_output=True, text=True,
                           env=env, cwd=ROOT, timeout=1500)
 
@@ -54,6 +55,9 @@ def test_gpu_suite_subset_and_model_cases_pass_on_the_host_model(model, order):
     assert "TEST INFRASTRUCTURE" in r.stderr or "passed" in r.stdout
     r = run_pytest(model, order, "tests/host_emu/model_cases.py")
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-1500:]
+    # model-based fuzzing of the batched ABI: random call sequences, valid and refused, against the header's contract
+    r = run_pytest(model, order, "tests/host_emu/model_fuzz.py", seeds=range(1, 41))
+    assert r.returncode == 0 and "40 passed" in r.stdout, r.stdout[-3000:] + r.stderr[-1500:]
 
 
 def test_the_same_under_address_and_undefined_behaviour_sanitizers(tmp_path):
@@ -66,7 +70,9 @@ def test_the_same_under_address_and_undefined_behaviour_sanitizers(tmp_path):
     lib = build(tmp_path, name="libaecm_b200_hostmodel_asan.so", extra=("-fsanitize=address,undefined", "-fno-sanitize-recover=undefined"))
     env = dict(os.environ, AECM_B200_LIB=lib, FAKE_CUDA_ORDER="random:3", FAKE_CUDA_DEVICES="2", LD_PRELOAD=libasan,
                ASAN_OPTIONS="detect_leaks=0:abort_on_error=1")
-    for args in (["tests/test_gpu_parity.py", "tests/test_gpu_scalar_api.py", "-m", "gpu", "-k", GPU_SUITE_SUBSET], ["tests/host_emu/model_cases.py"]):
+    env["MODEL_FUZZ_SEEDS"] = ",".join(map(str, range(41, 81)))
+    for args in (["tests/test_gpu_parity.py", "tests/test_gpu_scalar_api.py", "-m", "gpu", "-k", GPU_SUITE_SUBSET], ["tests/host_emu/model_cases.py"],
+                 ["tests/host_emu/model_fuzz.py"]):
         r = subprocess.run([sys.executable, "-m", "pytest", "-q", "-x", "-p", "no:cacheprovider", *args], capture_output=True, text=True, env=env,
                            cwd=ROOT, timeout=1500)
         assert r.returncode == 0 and "AddressSanitizer" not in r.stderr and "runtime error:" not in r.stderr, r.stdout[-2000:] + r.stderr[-3000:]
@@ -82,6 +88,8 @@ MUTANTS = {
     # main-stream work (here: a state read-back) no longer waits for the kernels of earlier submissions
     "main_stream_follows_slots": ("        CU(b, cudaStreamWaitEvent(b->stream, b->last_kernel, 0));", "        (void)0;", "lazy",
                                   ["tests/host_emu/model_cases.py", "-k", "main_stream_calls_see"]),
+    # not a dependency but a check: a repeated instanceIndex is no longer refused (two rows would race on one record)
+    "duplicate_index_accepted": ("rc = AECM_BAD_PARAMETER_ERROR; /* duplicate */", "rc = 0;", "eager", ["tests/host_emu/model_fuzz.py"]),
 }
 
 
