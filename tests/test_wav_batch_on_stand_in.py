@@ -24,12 +24,19 @@ SAN = {"asan_ubsan": (["-fsanitize=address,undefined", "-fno-sanitize-recover=un
        "tsan": (["-fsanitize=thread"], "WARNING: ThreadSanitizer", "WARNING: ThreadSanitizer")}
 
 
-@pytest.fixture(scope="module", params=sorted(SAN))
+# what lies below the tool: the stand-in batch (fake_batch.c), or the product's own csrc/aecm_batch.c on the modelled CUDA runtime
+# (host_model.c, lazy execution) -- then the batch layer's staging, slots and events are under the sanitizer as well
+BELOW = {"stand_in": [os.path.join(HERE, "host_emu", "fake_batch.c")],
+         "host_model": [os.path.join(ROOT, "webrtc_aecm_b200", "csrc", "aecm_batch.c"), os.path.join(HERE, "host_emu", "host_model.c")]}
+
+
+@pytest.fixture(scope="module", params=[(s_, b_) for s_ in sorted(SAN) for b_ in sorted(BELOW)], ids=lambda p: f"{p[0]}-{p[1]}")
 def tool(request, tmp_path_factory):
-    flags, *marks = SAN[request.param]
-    exe = str(tmp_path_factory.mktemp("wavtool") / f"aecm_wav_batch_{request.param}")
-    cmd = ["gcc", *flags, "-O1", "-g", "-std=gnu11", "-I", os.path.join(ROOT, "include"), "-I", os.path.join(ROOT, "webrtc_aecm_b200", "csrc"),
-           os.path.join(ROOT, "webrtc_aecm_b200", "csrc", "aecm_wav_batch.c"), os.path.join(HERE, "host_emu", "fake_batch.c"),
+    san, below = request.param
+    flags, *marks = SAN[san]
+    exe = str(tmp_path_factory.mktemp("wavtool") / f"aecm_wav_batch_{san}_{below}")
+    cmd = ["gcc", *flags, "-O1", "-g", "-std=gnu11", "-I", os.path.join(HERE, "host_emu", "fake_cuda"), "-I", os.path.join(ROOT, "include"),
+           "-I", os.path.join(ROOT, "webrtc_aecm_b200", "csrc"), os.path.join(ROOT, "webrtc_aecm_b200", "csrc", "aecm_wav_batch.c"), *BELOW[below],
            os.path.join(ROOT, "oracle", "aecm_oracle.c"), "-o", exe, "-lpthread", "-lm"]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0 and "san" in r.stderr.lower() and "cannot find" in r.stderr.lower():
