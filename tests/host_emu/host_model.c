@@ -372,7 +372,12 @@ cudaError_t cudaFree(void *p) {
     return cudaSuccess;
 }
 cudaError_t cudaMallocHost(void **p, size_t bytes) {
-    Pinned *h = (Pinned *)calloc(1, sizeof(*h));
+    Pinned *h;
+    if (host_model_take_malloc_failure()) {
+        *p = NULL;
+        return err(cudaErrorMemoryAllocation);
+    }
+    h = (Pinned *)calloc(1, sizeof(*h));
     *p = malloc(bytes ? bytes : 1);
     if (!*p || !h) { free(h); return err(cudaErrorMemoryAllocation); }
     memset(*p, 0x5A, bytes);

@@ -174,3 +174,125 @@ def test_main_stream_calls_see_the_state_left_by_a_submission_in_flight():
     b.close()
     for p in (pf, pn, po):
         L.AecmB200_HostFree(p)
+
+
+def test_create_survives_an_allocation_failure_at_every_point():
+    """AecmB200_Create makes about twenty device allocations; whichever of them fails, it must return NULL after releasing what it
+    already had (the sanitizer build of this test checks the releasing), and a later Create must work."""
+    L.AecmB200_Create.restype = C.c_void_p
+    L.AecmB200_Free.argtypes = [C.c_void_p]
+    failed = 0
+    for k in range(1, 40):
+        M.host_model_fail_malloc_in(k)
+        h = L.AecmB200_Create(5, 0)
+        if h:
+            L.AecmB200_Free(h)
+            break
+        failed += 1
+    M.host_model_fail_malloc_in(0)
+    assert 10 <= failed < 39, failed
+    b = AecmBatch(5, 0)
+    assert b.init(16000) == 0
+    b.close()
+
+
+def test_group_create_fails_cleanly_when_a_shard_cannot_be_built():
+    L.AecmB200_GroupCreate.restype = C.c_void_p
+    L.AecmB200_GroupFree.argtypes = [C.c_void_p]
+    devices = (C.c_int32 * 2)(0, 1)
+    M.host_model_fail_malloc_in(25)  # inside the second shard's Create
+    assert not L.AecmB200_GroupCreate(10, 2, devices)
+    M.host_model_fail_malloc_in(0)
+    assert not L.AecmB200_GroupCreate(1, 2, devices)  # more shards than instances
+    bad = (C.c_int32 * 2)(0, 7)
+    assert not L.AecmB200_GroupCreate(10, 2, bad)  # no such device
+    g = L.AecmB200_GroupCreate(10, 2, devices)
+    assert g
+    L.AecmB200_GroupFree(g)
+
+
+def test_device_plane_calls_interleaved_with_host_plane_submissions():
+    """AecmB200_ProcessStreamDevice works on the batch's main stream, the host-plane calls on the slot streams; alternating them
+    call by call crosses the hand-over in both directions every time.  (On the model any host array is "device" memory.)"""
+    fs, spc, n, calls = 16000, 160, 5, 40
+    far, near = synth_streams(n, calls * spc, fs, seed=321, delay_ms=np.arange(n) * 11)
+    want, _, _ = ol.run_streams(far, near, fs=fs, impl="oracle")
+    b = AecmBatch(n, 0)
+    assert L.AecmB200_NumInstances(b._h) == n and L.AecmB200_Device(b._h) == 0 and b.cuda_stream()
+    L.AecmB200_LastError.restype = C.c_char_p
+    assert L.AecmB200_LastError(b._h) == b"" and L.AecmB200_LastError(None) == b"null batch"
+    assert b.init(fs) == 0
+    out = np.zeros_like(near)
+    st = np.zeros(n, dtype=np.int32)
+    c = 0
+    while c < calls:
+        k = 1 + (c % 3 == 2 and c + 2 <= calls)  # sometimes two fused calls
+        f = np.ascontiguousarray(far[:, c * spc:(c + k) * spc])
+        x = np.ascontiguousarray(near[:, c * spc:(c + k) * spc])
+        o = np.zeros_like(x)
+        a = api.StreamArgs(f.ctypes.data, x.ctypes.data, None, o.ctypes.data, k * spc, 0, n, spc, k, None, 40, None, st.ctypes.data)
+        if (c // 2) % 2:
+            assert L.AecmB200_ProcessStreamDevice(b._h, C.byref(a)) == 0
+            b.synchronize()
+        else:
+            slot = c % L.AecmB200_NumStreamSlots()
+            assert L.AecmB200_SubmitStream(b._h, C.byref(a), slot) == 0
+            assert L.AecmB200_WaitStream(b._h, slot) == 0
+        assert not st.any()
+        out[:, c * spc:(c + k) * spc] = o
+        c += k
+    np.testing.assert_array_equal(out, want)
+    rc, d, q = b.delay_estimate()
+    assert rc == 0 and len(d) == n and (d >= -2).all() and (q >= 0).all()
+    b.close()
+
+
+def test_trace_mode_runs(monkeypatch, capfd):
+    monkeypatch.setenv("AECM_B200_TRACE", "1")
+    b = AecmBatch(3, 0)
+    assert b.init(16000) == 0
+    x = np.zeros((3, 160), dtype=np.int16)
+    rc, out, st = b.process_stream(x, x)
+    assert rc == 0 and not st.any()
+    b.close()
+    assert "aecm_b200 trace slot" in capfd.readouterr().err
+
+
+def test_scalar_create_fails_cleanly_when_the_pool_cannot_be_built():
+    S = api.scalar_api()
+    S.WebRtcAecm_Create.restype = C.c_void_p
+    S.WebRtcAecm_Free.argtypes = [C.c_void_p]
+    first = S.WebRtcAecm_Create()  # makes sure a pool exists, then fill it so that the next Create needs a new pool
+    assert first
+    rest = [S.WebRtcAecm_Create() for _ in range(255)]
+    assert all(rest)
+    M.host_model_fail_malloc_in(3)
+    assert not S.WebRtcAecm_Create()
+    M.host_model_fail_malloc_in(0)
+    h = S.WebRtcAecm_Create()
+    assert h
+    for p in [first, h, *rest]:
+        S.WebRtcAecm_Free(p)
+
+
+def test_adopted_stream_launch_counter_and_selftests():
+    """AecmB200_AdoptCudaStream: the batch moves to a stream the caller owns (here one made by the modelled runtime), which it
+    must neither destroy nor outlive; plus the launch counter and the self-test entry points (the oracle answers on the model)."""
+    s = C.c_void_p()
+    assert M.cudaStreamCreateWithFlags(C.byref(s), 1) == 0
+    L.AecmB200_KernelLaunchCount.restype = C.c_int64
+    before = L.AecmB200_KernelLaunchCount()
+    b = AecmBatch(3, 0)
+    b.adopt_cuda_stream(s.value)
+    assert b.cuda_stream() == s.value
+    assert b.init(16000) == 0
+    x = np.zeros((3, 160), dtype=np.int16)
+    a = api.StreamArgs(x.ctypes.data, x.ctypes.data, None, np.zeros_like(x).ctypes.data, 160, 0, 3, 160, 1, None, 40, None, None)
+    assert L.AecmB200_ProcessStreamDevice(b._h, C.byref(a)) == 0
+    b.synchronize()
+    b.close()
+    M.cudaStreamDestroy.argtypes = [C.c_void_p]
+    assert M.cudaStreamDestroy(s) == 0  # still the caller's to destroy
+    assert L.AecmB200_KernelLaunchCount() >= before + 2
+    L.AecmB200_SelfTestSqrtFloor.restype = C.c_int64
+    assert L.AecmB200_SelfTestSqrtFloor(0, 1 << 24) == 0
