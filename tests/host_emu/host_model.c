@@ -104,6 +104,10 @@ __attribute__((constructor)) static void announce(void) {
         g_mode = 2;
         g_rng = m[6] == ':' ? (uint32_t)atoi(m + 7) * 2654435761u + 1u : 12345u;
     }
+    if (getenv("FAKE_CUDA_FAIL_MALLOC_IN")) { /* for programs that cannot call host_model_fail_malloc_in() themselves */
+        extern void host_model_fail_malloc_in(int n);
+        host_model_fail_malloc_in(atoi(getenv("FAKE_CUDA_FAIL_MALLOC_IN")));
+    }
     fprintf(stderr, "aecm host model loaded: TEST INFRASTRUCTURE (oracle behind a modelled CUDA runtime, %s execution) -- not the product\n",
             g_mode == 0 ? "lazy" : g_mode == 1 ? "eager" : "random");
 }
