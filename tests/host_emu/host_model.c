@@ -680,9 +680,12 @@ void host_model_free_touching(void *a) {
     unlock();
     free(a);
 }
-static int g_fail_malloc_in = 0; /* > 0: the n-th cudaMalloc from now fails once */
-void host_model_fail_malloc_in(int n) { g_fail_malloc_in = n; }
-int host_model_take_malloc_failure(void) { return g_fail_malloc_in > 0 && --g_fail_malloc_in == 0; }
+static int g_fail_malloc_in = 0; /* > 0: the n-th device / pinned allocation from now fails once (allocations come from many threads) */
+void host_model_fail_malloc_in(int n) { __atomic_store_n(&g_fail_malloc_in, n, __ATOMIC_SEQ_CST); }
+int host_model_take_malloc_failure(void) {
+    if (__atomic_load_n(&g_fail_malloc_in, __ATOMIC_SEQ_CST) <= 0) return 0;
+    return __atomic_sub_fetch(&g_fail_malloc_in, 1, __ATOMIC_SEQ_CST) == 0;
+}
 int host_model_current_device(void) { return t_device; }
 long host_model_pending_ops(void) {
     long n = 0;

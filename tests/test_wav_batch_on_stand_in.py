@@ -90,3 +90,30 @@ def test_one_unreadable_pair_costs_only_its_own_output(tool, tmp_path):
     assert "1 pair(s) unreadable" in res.stderr and "4 pairs written" in res.stdout
     for d in pairs:
         assert open(d / "near_out.wav", "rb").read() == want[d.name], d.name
+
+
+@pytest.mark.parametrize("fail_in", [3, 24, 27, 30])
+def test_a_shard_that_loses_an_allocation_costs_only_its_own_pairs(tool, tmp_path, fail_in):
+    """Two shards on two (modelled) devices; the fail_in-th device or pinned allocation of the process fails -- while a batch is
+    created, while a shard sets up its staging, or inside a submission.  The tool must say which shard lost its pairs, exit 1,
+    still write every other pair byte-identical to the reference CLI, and release everything (leak check on under ASan)."""
+    exe, _ = tool
+    if "host_model" not in exe:
+        pytest.skip("allocation failures are injected by the modelled CUDA runtime")
+    pairs = make_pairs(tmp_path, 6, seed=13)
+    want = reference_outputs(pairs, tmp_path)
+    args = []
+    for d in pairs:
+        args += [d / "far.wav", d / "near.wav"]
+    os.environ["FAKE_CUDA_FAIL_MALLOC_IN"] = str(fail_in)
+    try:
+        res = run(tool, "--devices", "0,1", *args)
+    finally:
+        del os.environ["FAKE_CUDA_FAIL_MALLOC_IN"]
+    assert res.returncode == 1 and "get no output" in res.stderr, (res.stdout, res.stderr[-2000:])
+    written = 0
+    for d in pairs:
+        if (d / "near_out.wav").exists():
+            assert open(d / "near_out.wav", "rb").read() == want[d.name], d.name
+            written += 1
+    assert 0 < written < len(pairs)
