@@ -74,6 +74,7 @@ int main(int argc, char **argv) {
     printf("%d instances x %d ticks of 10 ms in %.3f s (%.0f x real time per instance), %ld non-zero statuses\n", n, ticks,
            now_s() - t0, ticks * 0.01 / (now_s() - t0), nonzero);
     for (s = 0; s < slots; s++) { AecmB200_HostFree(in[s]); AecmB200_HostFree(out[s]); free(status[s]); }
+    free(in); free(out); free(status);
     AecmB200_Free(b);
     return 0;
 }
