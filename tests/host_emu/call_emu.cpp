@@ -39,6 +39,12 @@ int emu_norm_u32(unsigned a) { return norm_u32(a); }
 int emu_norm_w16(int a) { return norm_w16(a); }
 int emu_log_energy_q8(unsigned e, int q) { return log_energy_q8(e, q); }
 int emu_add_sat32(int a, int b) { return add_sat32(a, b); }
+// the comfort-noise generator as the device draws it (aecm_block.cuh: lane-parallel jump-ahead): out[k] = the (k+1)-th number
+// of WebRtcSpl_RandUArray started at `seed`, k = 0..63; returns the seed after 64 draws
+uint32_t emu_lcg_draws(uint32_t seed, int16_t *out) {
+    for (int k = 0; k < 64; k++) out[k] = (int16_t)(((kLcgJump.mul[k] * seed + kLcgJump.add[k]) & 0x7fffffffu) >> 16);
+    return (kLcgJump.mul[63] * seed + kLcgJump.add[63]) & 0x7fffffffu;
+}
 
 // One instance, n_calls API calls of `spc` samples.  ms: per-call msInSndCardBuf [n_calls].  far_ops: per call how
 // many times BufferFarend runs before Process (0 = underrun, 1 = normal, 2 = overrun).  Returns the OR of all return

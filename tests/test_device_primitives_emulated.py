@@ -73,3 +73,24 @@ def test_norms_sqrt_log_and_saturation_match_the_oracle(emu):  # noqa: F811
                 frac = (((e << z) & 0x7FFFFFFF) >> 23)
                 want = ((896 + ((31 - z) << 8) + frac - (q << 8) + 32768) & 0xFFFF) - 32768
             assert emu.emu_log_energy_q8(C.c_uint(e), q) == want, (e, q)
+
+
+def test_lcg_jump_ahead_equals_the_references_generator(emu):  # noqa: F811
+    """The device draws the k-th comfort-noise number directly (seed * A^k + C_k mod 2^31, a compile-time table) instead of
+    stepping the generator 64 times: against WebRtcSpl_RandUArray's own outputs (tests/golden/vectors.npz, generated from the
+    reference, signal_processing_library.cc:126-147) and against the oracle's stepping generator on random seeds."""
+    vec = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "vectors.npz"))
+    emu.emu_lcg_draws.restype = C.c_uint32
+    O = ol.oracle()
+    rng = np.random.default_rng(11)
+    seeds = [(int(s), np.asarray(w), int(a)) for s, w, a in zip(vec["rand_seed"], vec["rand_out"], vec["rand_seed_after"])]
+    for s in [666, 0, 1, 0x7FFFFFFF] + [int(x) for x in rng.integers(0, 1 << 31, 200)]:
+        buf = np.zeros(64, dtype=np.int16)
+        sd = C.c_uint32(s)
+        O.oracle_rand_u_array(buf.ctypes.data_as(C.c_void_p), 64, C.byref(sd))
+        seeds.append((s, buf, sd.value))
+    assert len(seeds) > 200
+    for s, want, after in seeds:
+        got = np.zeros(64, dtype=np.int16)
+        assert emu.emu_lcg_draws(C.c_uint32(s), got.ctypes.data_as(C.c_void_p)) == after, s
+        np.testing.assert_array_equal(got, want[:64])
