@@ -223,6 +223,8 @@ def test_random_delay_estimator_option_changes_on_emulated_warp(emu, seed):
         elif u < 0.04:
             max_la = int(rng.integers(0, 12))
             events.append((c, 0, int(rng.integers(0, 2)), 0, max_la, -1))
+    events += [(50, 1, 1, 0, 0, 0), (51, 1, -1, 0, 0, 0), (52, 1, 0, 0, 0, 0)]  # the smallest shifts: one block forward, one back, none
+    events.sort(key=lambda e: e[0])
     ev = np.ascontiguousarray(np.array(events, dtype=np.int32))
     # the oracle, stepped call by call with the same events
     o = ol.OracleInstance(fs, 1, 3)

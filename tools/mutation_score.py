@@ -163,6 +163,8 @@ def expected_extra():
             elif u < 0.06:
                 max_la = int(rng.integers(0, 12))
                 events.append((c, 0, int(rng.integers(0, 2)), 0, max_la, -1))
+        events += [(50, 1, 1, 0, 0, 0), (51, 1, -1, 0, 0, 0), (52, 1, 0, 0, 0, 0)]  # the smallest shifts
+        events.sort(key=lambda e: e[0])
         o = ol.OracleInstance(fs, 1, 3)
         soft = ol.oracle().oracle_aecm_soft_reset_delay_estimator
         soft.argtypes = [C.c_void_p, C.c_int]
