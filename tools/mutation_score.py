@@ -295,6 +295,11 @@ def run_cases(lib_path, names):
         out, acc, _ = t.emu_run(lib, case, far, near, clean, ms, inst)
         if not np.array_equal(out, want[inst]) or (acc != 0) != (ret[inst] != 0):
             os._exit(1)
+    for name in ("8k_far_underrun_ms_mix", "16k_stress_clean_cng_off_mode4", "16k_80_sample_calls"):  # planes at odd int16 positions: the 16-bit movers
+        case, far, near, clean, ms, want, ret = expected()[name]
+        out, acc, _ = t.emu_run(lib, case, far, near, clean, ms, 0, misalign=True)
+        if not np.array_equal(out, want[0]):
+            os._exit(1)
     x = expected_extra()
     for cfg, case, far, near, ms, want, trace in x["dly"]:
         inst = cfg["instances"][0]
