@@ -147,7 +147,7 @@ def test_delay_estimator_options_on_emulated_warp(emu, cfg):
         assert acc == 0 and ret[instance] == 0
 
 
-@pytest.mark.parametrize("seed,fs", [(s, f) for s, f in __import__("test_fuzz_api").SCRIPTS if s % 3 != 2][:14])
+@pytest.mark.parametrize("seed,fs", [(s, f) for s, f in __import__("test_fuzz_api").SCRIPTS if s % 3 != 2][:14] + __import__("test_fuzz_api").MUTANT_KILLERS)
 def test_random_call_sequences_on_emulated_warp(emu, seed, fs):
     """The randomised API scripts of tests/test_fuzz_api.py (mixed 80/160-sample calls, msInSndCardBuf jumps and clamps,
     under- and overruns, clean plane or not, all echo modes) through the device code on the emulated warp: output and the OR

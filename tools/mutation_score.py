@@ -138,9 +138,10 @@ def expected_extra():
         dly.append((cfg, dict(by["c5_delay_sweep_0_120ms"], fs=fs, spc=spc), far, near, ms, want, trace))
     _extra["dly"] = dly
     ctl = []
-    for seed, fs in [(2, 16000), (6, 8000), (14, 16000)] + [(sd, 8000 if sd % 3 == 0 else 16000) for sd in range(21, 45)]:
-        sc = fz.make_script(seed, 400, fs)
-        ev = (fz.make_control_events(seed, 400) + [(77, 2, 1, 0), (78, 2, 0, 4), (79, 2, 1, -1), (80, 2, 1, 5)]) if seed % 2 == 0 else []
+    for seed, fs in [(2, 16000), (6, 8000), (14, 16000)] + [(sd, 8000 if sd % 3 == 0 else 16000) for sd in range(21, 45)] + list(fz.MUTANT_KILLERS):
+        killer = (seed, fs) in fz.MUTANT_KILLERS  # these run as the test suite runs them: 500 calls, no control events
+        sc = fz.make_script(seed, 500 if killer else 400, fs)
+        ev = (fz.make_control_events(seed, 400) + [(77, 2, 1, 0), (78, 2, 0, 4), (79, 2, 1, -1), (80, 2, 1, 5)]) if seed % 2 == 0 and not killer else []
         ev.sort(key=lambda e: e[0])
         rcs = []
         want, want_rc = fz.run_oracle(sc, ev, rcs)
@@ -421,7 +422,7 @@ def main():
     out = ["# Mutation score of the parity cases on the device code (tools/mutation_score.py)", "",
            f"{len(sites)} mutation sites in {', '.join(FILES)}; {len(res)} drawn at random (seed {a.seed}); {n.get('does not compile', 0)} do not compile.",
            f"Of the {valid} valid mutants **{killed} are killed** ({100.0 * killed / max(valid, 1):.1f} %) by {len(CASE_ORDER)} case families, 8 delay-estimator configurations (delay trace "
-           f"per call), 27 random API scripts (half of them with control calls in mid-stream), 2 scripts with random option changes (float quality per call), the final records of 3 streams field by field, "
+           f"per call), 32 random API scripts (half of them with control calls in mid-stream), 2 scripts with random option changes (float quality per call), the final records of 3 streams field by field, "
            f"the FFT known answers of the reference and the scalar-primitive known answers, all on the emulated warp "
            f"(one instance each; {n.get('killed (hang)', 0)} by hanging, {n.get('killed (crash)', 0)} by crashing), {n.get('SURVIVED', 0)} survive:", ""]
     out += [f"* {d}" for _, v, d, _ in res if v == "SURVIVED"]
