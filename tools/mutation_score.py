@@ -148,20 +148,20 @@ def expected_extra():
         ctl.append((sc, ev, want, int(np.bitwise_or.reduce(want_rc)), rcs))
     _extra["ctl"] = ctl
     opt = []
-    for seed in (200, 203):
+    for seed in (201, 203):  # two of the suite's own option-change scripts (tests/test_call_path_emulated_warp.py), same generator
         rng = np.random.default_rng(seed)
-        fs, spc, calls = 16000, 160, 400
+        fs, spc, calls = 16000, 160, 500
         far, near = synth_streams(1, calls * spc, fs, seed=seed, delay_ms=int(rng.integers(0, 115)))
         far, near = np.ascontiguousarray(far[0]), np.ascontiguousarray(near[0])
         max_la = int(rng.integers(0, 9))
         events = [(0, 0, int(rng.integers(0, 2)), int(rng.integers(0, 4)), max_la, -1)]
         for c in range(1, calls):
             u = rng.random()
-            if u < 0.03:
+            if u < 0.02:
                 events.append((c, 0, int(rng.integers(0, 2)), int(rng.integers(0, 5)), -1, int(rng.integers(-1, max_la + 3))))
-            elif u < 0.05:
+            elif u < 0.035:
                 events.append((c, 1, int(rng.integers(-30, 31)), 0, 0, 0))
-            elif u < 0.06:
+            elif u < 0.04:
                 max_la = int(rng.integers(0, 12))
                 events.append((c, 0, int(rng.integers(0, 2)), 0, max_la, -1))
         events += [(50, 1, 1, 0, 0, 0), (51, 1, -1, 0, 0, 0), (52, 1, 0, 0, 0, 0)]  # the smallest shifts
