@@ -202,6 +202,28 @@ def test_random_control_calls_in_mid_stream_on_emulated_warp(emu, seed, fs):
     assert acc == int(np.bitwise_or.reduce(rcs))
 
 
+@pytest.mark.parametrize("fs,base_ms", [(16000, 20), (8000, 12), (16000, 29), (16000, 25)])
+def test_startup_stability_check_at_exactly_the_tolerance_on_emulated_warp(emu, fs, base_ms):
+    """tests/test_fuzz_api.tolerance_script (deviation == tolerance during start-up) through the device code; a tolerance of 9
+    instead of 8 in aecm_frame_api.cuh survives everything else in the suite."""
+    import test_fuzz_api as fz
+
+    s = fz.tolerance_script(fs, base_ms)
+    want, rcs = fz.run_oracle(s)
+    out = np.zeros_like(s["near"])
+    ms16 = np.ascontiguousarray(s["ms"].astype(np.int16))
+    spc_calls = np.ascontiguousarray(s["n"].astype(np.int32))
+    ops = np.ascontiguousarray(s["far_ops"])
+    cl = np.ascontiguousarray(s["cln"]) if s["clean"].all() else None
+    far, near = np.ascontiguousarray(s["far"]), np.ascontiguousarray(s["near"])
+    nbar = C.c_long(0)
+    vp = lambda a: None if a is None else a.ctypes.data_as(C.c_void_p)
+    acc = emu.emu_run_stream(fs, s["cng"], s["echo_mode"], vp(far), vp(near), vp(cl), vp(out), len(s["n"]), 0, vp(ms16), vp(ops), None, C.byref(nbar),
+                             None, None, vp(spc_calls), None, 0, None, None)
+    np.testing.assert_array_equal(out, want)
+    assert acc == int(np.bitwise_or.reduce(rcs))
+
+
 @pytest.mark.parametrize("seed", range(200, 208))
 def test_random_delay_estimator_option_changes_on_emulated_warp(emu, seed):
     """SURVEY 8-f4 device functions under random use: the estimator's setters, soft resets by random shifts and re-creations

@@ -185,6 +185,28 @@ def test_control_events_cover_their_kinds():
     assert kinds == {2, 3, 4} and refused >= 10
 
 
+def tolerance_script(fs, base_ms):
+    """msInSndCardBuf alternating between base_ms and base_ms + 8 during start-up: the deviation from the first value is EXACTLY the
+    tolerance of the buffer-size stability check for small values (max(0.2 * ms, 8), echo_control_mobile.cc:305-337; `dev < tol`
+    is a double comparison there), so every second call restarts the count until the script settles on base_ms."""
+    s = make_script(7, 300, fs)
+    ms = np.full(300, base_ms, dtype=np.int32)
+    ms[1:80:2] = base_ms + 8
+    return dict(s, ms=ms, far_ops=np.ones(300, dtype=np.uint8))
+
+
+@pytest.mark.skipif(ol.ref_path() is None, reason="oracle/_ref/libaecm_ref.so not built (needs /root/reference)")
+@pytest.mark.parametrize("fs,base_ms", [(16000, 20), (8000, 12), (16000, 29), (16000, 25)])
+def test_startup_stability_check_at_exactly_the_tolerance(fs, base_ms):
+    s = tolerance_script(fs, base_ms)
+    a, ra = run_oracle(s)
+    b, rb = run_reference(s)
+    np.testing.assert_array_equal(ra, rb)
+    np.testing.assert_array_equal(a, b)
+    steady = dict(s, ms=np.full(300, base_ms, dtype=np.int32))
+    assert not np.array_equal(run_oracle(steady)[0], a)  # the restarts really delay the end of start-up
+
+
 def test_scripts_exercise_what_they_claim():
     """Across the scripts: both frame sizes at both rates, under- and overruns, clamped ms, clean planes, all echo modes."""
     seen = {"mixed": 0, "under": 0, "over": 0, "clamp": 0, "clean": 0}

@@ -146,6 +146,10 @@ def expected_extra():
         rcs = []
         want, want_rc = fz.run_oracle(sc, ev, rcs)
         ctl.append((sc, ev, want, int(np.bitwise_or.reduce(want_rc)), rcs))
+    for fs, base in ((16000, 20), (8000, 12), (16000, 29), (16000, 25)):  # the start-up stability check at exactly its tolerance
+        sc = fz.tolerance_script(fs, base)
+        want, want_rc = fz.run_oracle(sc)
+        ctl.append((sc, [], want, int(np.bitwise_or.reduce(want_rc)), []))
     _extra["ctl"] = ctl
     opt = []
     for seed in (201, 203):  # two of the suite's own option-change scripts (tests/test_call_path_emulated_warp.py), same generator
