@@ -50,7 +50,8 @@ def model(tmp_path_factory):
 
 @pytest.mark.parametrize("order", ["lazy", "eager", "random:1"])
 def test_gpu_suite_subset_and_model_cases_pass_on_the_host_model(model, order):
-    if order != "eager":  # eager execution is what the real GPU does to these tests every round; it only runs the model's own cases here
+    if order == "lazy":  # the GPU suite's own tests under the latest legal order (and, below, in random order under the sanitizers); the other
+        # orders run the model's own cases and the fuzzer -- eager execution is what the real GPU does to those tests every round anyway
         r = run_pytest(model, order, "tests/test_gpu_parity.py", "tests/test_gpu_scalar_api.py", "-m", "gpu", "-k", GPU_SUITE_SUBSET)
         assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-1500:]
     r = run_pytest(model, order, "tests/host_emu/model_cases.py")
